@@ -1,0 +1,13 @@
+"""
+iscc_search_b200 - B200-native exact NPHD / Hamming top-k backend for iscc-search.
+
+Public surface (mirrors what iscc-search imports from `iscc_usearch`):
+    ShardedNphdIndex, ShardedIndex128, Matches, BatchMatches, timer
+All search arithmetic runs in libisx_b200.so (hand-written sm_100a CUDA); there is no CPU path.
+"""
+
+from iscc_search_b200.matches import BatchMatches, Match, Matches  # noqa: F401
+from iscc_search_b200.nphd import ShardedIndex128, ShardedNphdIndex  # noqa: F401
+
+__all__ = ["ShardedNphdIndex", "ShardedIndex128", "Matches", "BatchMatches", "Match"]
+__version__ = "0.1.0"

@@ -1,0 +1,1063 @@
+// isx.cu - store management + C ABI of libisx_b200.so (see include/isx.h for the contract and the
+// reference interfaces each entry point replaces).
+//
+// Host side: exact key map, length buckets of plane-major segments in HBM, swap-remove (rows stay
+// dense, no tombstones in the scan), launch planning for the scan (bootstrap rounds that tighten
+// the per-query rank threshold before the bulk of the store is streamed), exact fallback re-scan
+// for queries whose candidate buffer overflowed.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <shared_mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/isx.h"
+#include "kernels.cuh"
+#include "keymap.hpp"
+
+namespace isx {
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(_e == cudaErrorMemoryAllocation ? ISX_ENOMEM : ISX_ECUDA, "%s failed: %s (%s:%d)", #expr, \
+                        cudaGetErrorString(_e), __FILE__, __LINE__);                               \
+    } while (0)
+
+constexpr uint32_t kMinSegRows = 4096;
+constexpr uint32_t kMaxSegRows = 1u << kRowBits;  // 4 Mi rows
+constexpr uint32_t kBlockRows = kRowsPerStep;     // 1024
+
+// growable device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        CU(cudaMalloc(&p, want));
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        CU(cudaMallocHost(&p, want));
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Segment {
+    void* d_mem = nullptr;  // one allocation: planes | khi | klo
+    SegDesc desc{};
+    uint32_t len_bytes = 0;
+    std::vector<uint64_t> h_khi, h_klo;  // host mirror of the keys (needed to re-point the moved row on swap-remove)
+    size_t bytes = 0;
+};
+
+// rank tables for one set of compared-length classes
+struct RankTables {
+    uint32_t class_mask = 0;  // bit m-1: m bytes compared
+    uint32_t R = 0;
+    std::vector<uint16_t> rank;  // [33][257]
+    std::vector<uint16_t> hmax;  // [33][R]
+    std::vector<uint32_t> frac_h, frac_n;  // representative fraction of every rank (for thresholds)
+    DevBuf d_rank, d_hmax;
+};
+
+}  // namespace isx
+
+using namespace isx;
+
+struct isx_store {
+    int device = 0;
+    uint32_t key_bytes = 8, max_bytes = 32, fixed_len = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    bool profiling = false;
+
+    std::shared_mutex rows_mu;  // shared: search/get/contains; exclusive: add/remove/clear/load
+    std::mutex work_mu;         // serialises users of the scratch buffers below
+
+    KeyMap map;
+    std::vector<Segment> segs;                 // global segment ids
+    std::vector<uint32_t> bucket_segs[kMaxBytes + 1];
+    uint64_t bucket_rows[kMaxBytes + 1] = {0};
+    uint64_t device_bytes = 0;
+    uint64_t version = 0;  // bumped by every mutation
+
+    // device mirrors
+    DevBuf d_segs;
+    bool segs_dirty = true;
+    DevBuf d_blocks;
+    uint64_t blocks_version = ~0ull;
+    std::vector<uint2> h_blocks;
+    uint32_t bucket_block_lo[kMaxBytes + 2] = {0};  // block range of bucket L: [lo[L], lo[L+1])
+
+    RankTables tables;
+
+    // scratch
+    DevBuf d_stage_codes, d_stage_keys, d_stage_dest, d_moves;
+    DevBuf d_queries, d_tau, d_hist, d_cnt, d_ovf, d_cand, d_qmap, d_fb, d_fb_cand;
+    DevBuf d_out_khi, d_out_klo, d_out_h, d_out_n, d_out_cnt, d_out_codes;
+    PinnedBuf h_queries, h_qmap, h_flags, h_out;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    isx_stats_t stats{};
+    int sm_count = 148;
+    int max_smem_optin = 0;
+};
+
+namespace isx {
+
+static inline Key128 load_key(const isx_store* s, const void* keys, size_t i) {
+    if (s->key_bytes == 8) return Key128{reinterpret_cast<const uint64_t*>(keys)[i], 0};
+    const uint8_t* kb = reinterpret_cast<const uint8_t*>(keys) + i * 16;
+    uint64_t hi = 0, lo = 0;
+    for (int b = 0; b < 8; b++) { hi = (hi << 8) | kb[b]; lo = (lo << 8) | kb[8 + b]; }
+    return Key128{hi, lo};
+}
+static inline void store_key(const isx_store* s, void* keys, size_t i, uint64_t hi, uint64_t lo) {
+    if (s->key_bytes == 8) { reinterpret_cast<uint64_t*>(keys)[i] = hi; return; }
+    uint8_t* kb = reinterpret_cast<uint8_t*>(keys) + i * 16;
+    for (int b = 0; b < 8; b++) { kb[b] = (uint8_t)(hi >> (56 - 8 * b)); kb[8 + b] = (uint8_t)(lo >> (56 - 8 * b)); }
+}
+
+static int set_device(isx_store* s) {
+    CU(cudaSetDevice(s->device));
+    return 0;
+}
+
+static int new_segment(isx_store* s, uint32_t len_bytes, uint32_t cap) {
+    if (s->segs.size() >= (1u << kSegBits)) return fail(ISX_ENOMEM, "segment table full (%u segments)", 1u << kSegBits);
+    Segment sg;
+    uint32_t words = (len_bytes + 3) / 4;
+    size_t plane_bytes = (size_t)words * cap * 4;
+    size_t key_bytes = (size_t)cap * 8;
+    size_t total = plane_bytes + key_bytes * (s->key_bytes == 16 ? 2 : 1);
+    CU(cudaMalloc(&sg.d_mem, total));
+    CU(cudaMemsetAsync(sg.d_mem, 0, total, s->stream));
+    sg.bytes = total;
+    sg.len_bytes = len_bytes;
+    sg.desc.planes = reinterpret_cast<uint32_t*>(sg.d_mem);
+    sg.desc.khi = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sg.d_mem) + plane_bytes);
+    sg.desc.klo = s->key_bytes == 16 ? sg.desc.khi + cap : nullptr;
+    sg.desc.cap = cap;
+    sg.desc.n = 0;
+    sg.desc.len_bytes = len_bytes;
+    sg.desc.words = words;
+    sg.h_khi.resize(cap);
+    if (s->key_bytes == 16) sg.h_klo.resize(cap);
+    s->device_bytes += total;
+    s->bucket_segs[len_bytes].push_back((uint32_t)s->segs.size());
+    s->segs.push_back(std::move(sg));
+    s->segs_dirty = true;
+    return 0;
+}
+
+static int upload_segs(isx_store* s) {
+    if (!s->segs_dirty) return 0;
+    size_t n = std::max<size_t>(s->segs.size(), 1);
+    std::vector<SegDesc> h(n);
+    for (size_t i = 0; i < s->segs.size(); i++) h[i] = s->segs[i].desc;
+    if (s->d_segs.ensure(n * sizeof(SegDesc))) return ISX_ECUDA;
+    // pageable source: cudaMemcpyAsync stages it before returning, so the vector may die afterwards
+    CU(cudaMemcpyAsync(s->d_segs.p, h.data(), n * sizeof(SegDesc), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    s->segs_dirty = false;
+    return 0;
+}
+
+static int upload_blocks(isx_store* s) {
+    if (s->blocks_version == s->version) return 0;
+    s->h_blocks.clear();
+    for (uint32_t L = 1; L <= kMaxBytes; L++) {
+        s->bucket_block_lo[L] = (uint32_t)s->h_blocks.size();
+        for (uint32_t sid : s->bucket_segs[L]) {
+            uint32_t n = s->segs[sid].desc.n;
+            for (uint32_t r = 0; r < n; r += kBlockRows) s->h_blocks.push_back(make_uint2(sid, r));
+        }
+    }
+    s->bucket_block_lo[kMaxBytes + 1] = (uint32_t)s->h_blocks.size();
+    size_t bytes = std::max<size_t>(s->h_blocks.size(), 1) * sizeof(uint2);
+    if (s->d_blocks.ensure(bytes)) return ISX_ECUDA;
+    if (!s->h_blocks.empty()) {
+        CU(cudaMemcpyAsync(s->d_blocks.p, s->h_blocks.data(), s->h_blocks.size() * sizeof(uint2), cudaMemcpyHostToDevice, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    s->blocks_version = s->version;
+    return 0;
+}
+
+// ---- rank tables -------------------------------------------------------------------------------
+// Dense rank of every rational h/(8m) over the compared-length classes in `mask`; exact integer
+// order via cross multiplication. hmax[m][r] = largest h with rank(m,h) <= r.
+static int build_tables(isx_store* s, uint32_t mask) {
+    RankTables& t = s->tables;
+    if (t.class_mask == mask && t.R) return 0;
+    struct F { uint32_t h, n, m; };
+    std::vector<F> fr;
+    for (uint32_t m = 1; m <= kMaxBytes; m++)
+        if (mask & (1u << (m - 1)))
+            for (uint32_t h = 0; h <= 8 * m; h++) fr.push_back(F{h, 8 * m, m});
+    std::sort(fr.begin(), fr.end(), [](const F& a, const F& b) {
+        uint64_t x = (uint64_t)a.h * b.n, y = (uint64_t)b.h * a.n;
+        if (x != y) return x < y;
+        return a.n < b.n;
+    });
+    t.rank.assign(33 * 257, 0xffff);
+    t.frac_h.clear();
+    t.frac_n.clear();
+    uint32_t r = 0;
+    for (size_t i = 0; i < fr.size(); i++) {
+        if (i > 0 && (uint64_t)fr[i].h * fr[i - 1].n != (uint64_t)fr[i - 1].h * fr[i].n) r++;
+        if (t.frac_h.size() <= r) { t.frac_h.push_back(fr[i].h); t.frac_n.push_back(fr[i].n); }
+        t.rank[fr[i].m * 257 + fr[i].h] = (uint16_t)r;
+    }
+    t.R = fr.empty() ? 1 : r + 1;
+    if (t.R >= (1u << kRankBits)) return fail(ISX_EINVAL, "too many distinct distances (%u)", t.R);
+    t.hmax.assign((size_t)33 * t.R, 0);
+    for (uint32_t m = 1; m <= kMaxBytes; m++) {
+        if (!(mask & (1u << (m - 1)))) continue;
+        uint32_t h = 0;
+        for (uint32_t rr = 0; rr < t.R; rr++) {
+            while (h + 1 <= 8 * m && t.rank[m * 257 + h + 1] <= rr) h++;
+            t.hmax[(size_t)m * t.R + rr] = (uint16_t)h;
+        }
+    }
+    if (t.d_rank.ensure(t.rank.size() * 2) || t.d_hmax.ensure(t.hmax.size() * 2)) return ISX_ECUDA;
+    CU(cudaMemcpyAsync(t.d_rank.p, t.rank.data(), t.rank.size() * 2, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(t.d_hmax.p, t.hmax.data(), t.hmax.size() * 2, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    t.class_mask = mask;
+    return 0;
+}
+
+// ---- scan launch dispatch ----------------------------------------------------------------------
+template <int WE, int G>
+static int launch_scan_t(isx_store* s, const ScanParams& p, uint32_t grid_cap_per_sm) {
+    constexpr int QW = (WE <= 4) ? 4 : 8;
+    size_t smem = (size_t)p.T * (QW * 4 + 4 + 1) + 16;
+    static bool attr_done = false;
+    if (!attr_done || smem > 48 * 1024) {
+        CU(cudaFuncSetAttribute(k_scan<WE, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem_optin));
+        attr_done = true;
+    }
+    uint32_t n_blocks = p.block_end - p.block_begin;
+    uint32_t n_items = (n_blocks + p.blocks_per_item - 1) / p.blocks_per_item;
+    uint32_t grid = std::min<uint32_t>(n_items, (uint32_t)s->sm_count * grid_cap_per_sm);
+    if (grid == 0) return 0;
+    k_scan<WE, G><<<grid, kThreads, smem, s->stream>>>(p);
+    CU(cudaGetLastError());
+    s->stats.kernel_launches++;
+    s->stats.scan_launches++;
+    return 0;
+}
+
+static uint32_t groups_for(uint32_t we) { return we <= 2 ? 4 : (we <= 4 ? 2 : 1); }
+
+static int launch_scan(isx_store* s, ScanParams& p, uint32_t we, uint32_t bpi_hint) {
+    uint32_t G = groups_for(we);
+    p.blocks_per_item = std::max(G, (bpi_hint / G) * G);
+    const uint32_t per_sm = 4;
+    switch (we) {
+        case 1: return launch_scan_t<1, 4>(s, p, per_sm);
+        case 2: return launch_scan_t<2, 4>(s, p, per_sm);
+        case 3: return launch_scan_t<3, 2>(s, p, per_sm);
+        case 4: return launch_scan_t<4, 2>(s, p, per_sm);
+        case 5: return launch_scan_t<5, 1>(s, p, per_sm);
+        case 6: return launch_scan_t<6, 1>(s, p, per_sm);
+        case 7: return launch_scan_t<7, 1>(s, p, per_sm);
+        case 8: return launch_scan_t<8, 1>(s, p, per_sm);
+    }
+    return fail(ISX_EINVAL, "bad word count %u", we);
+}
+
+// Scan block range [b0, b1) of the global block list for one tile of queries; the range may span
+// several buckets, each bucket portion is one launch (uniform compared length).
+static int scan_range(isx_store* s, ScanParams& p, uint32_t b0, uint32_t b1, uint32_t bpi_hint) {
+    for (uint32_t L = 1; L <= kMaxBytes; L++) {
+        uint32_t lo = std::max(b0, s->bucket_block_lo[L]), hi = std::min(b1, s->bucket_block_lo[L + 1]);
+        if (lo >= hi) continue;
+        uint32_t m = std::min(p.qlen_bytes, L);
+        p.block_begin = lo;
+        p.block_end = hi;
+        int rc = launch_scan(s, p, (m + 3) / 4, bpi_hint);
+        if (rc) return rc;
+        uint64_t rows = 0;  // live rows in the range (last block of a segment may be partial)
+        for (uint32_t b = lo; b < hi; b++) {
+            const SegDesc& d = s->segs[s->h_blocks[b].x].desc;
+            rows += std::min<uint32_t>(kBlockRows, d.n - s->h_blocks[b].y);
+        }
+        s->stats.pairs += rows * p.T;
+        s->stats.algo_bytes += rows * m;
+        s->stats.algo_popc += rows * p.T * ((m + 3) / 4);
+    }
+    return 0;
+}
+
+static size_t select_smem(uint32_t cap, uint32_t key_words) { return (size_t)cap * (8 * key_words + 12) + 64; }
+
+static uint32_t max_sort_cap(const isx_store* s) {
+    uint32_t key_words = s->key_bytes == 16 ? 2 : 1;
+    uint32_t cap = 1024;
+    while (select_smem(cap * 2, key_words) + 2048 <= (size_t)s->max_smem_optin) cap *= 2;
+    return cap;
+}
+
+struct SearchOut {
+    uint64_t* khi; uint64_t* klo; uint16_t* h; uint16_t* n; uint32_t* cnt; uint8_t* codes;
+};
+
+// Core: all pointers in `out` are DEVICE pointers laid out [Q][k]. `queries` host or device.
+static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, const uint8_t* qlens, size_t Q, uint32_t k,
+                       uint32_t thr_num, uint32_t thr_den, const SearchOut& out) {
+    isx_stats_t& st = s->stats;
+    st = isx_stats_t{};
+    if (Q == 0) return 0;
+    if (k < 1) return fail(ISX_EINVAL, "`count` must be >= 1");
+    const uint32_t key_words = s->key_bytes == 16 ? 2 : 1;
+    const uint32_t cap_max = max_sort_cap(s);
+    if (k > cap_max) return fail(ISX_ELIMIT, "count %u exceeds the supported maximum %u", k, cap_max);
+    for (size_t i = 0; i < Q; i++) {
+        uint32_t L = qlens[i];
+        if (L < 1 || L > s->max_bytes) return fail(ISX_EINVAL, "query %zu: length %u bytes outside 1..%u", i, L, s->max_bytes);
+        if (s->fixed_len && L != s->fixed_len) return fail(ISX_EINVAL, "query %zu: length %u bytes, index expects %u", i, L, s->fixed_len);
+    }
+    int rc;
+    if ((rc = upload_segs(s)) || (rc = upload_blocks(s))) return rc;
+    const uint32_t n_blocks_total = (uint32_t)s->h_blocks.size();
+
+    // group queries by length (stable): order[] lists original indices
+    std::vector<uint32_t> order(Q);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return qlens[a] < qlens[b]; });
+
+    // compared-length classes present
+    uint32_t qmask = 0, bmask = 0, cmask = 0;
+    for (size_t i = 0; i < Q; i++) qmask |= 1u << (qlens[i] - 1);
+    for (uint32_t L = 1; L <= kMaxBytes; L++) if (s->bucket_rows[L]) bmask |= 1u << (L - 1);
+    for (uint32_t a = 1; a <= kMaxBytes; a++) {
+        if (!(qmask & (1u << (a - 1)))) continue;
+        cmask |= 1u << (a - 1);  // keeps the table non-empty for an empty store
+        for (uint32_t b = 1; b <= kMaxBytes; b++)
+            if (bmask & (1u << (b - 1))) cmask |= 1u << (std::min(a, b) - 1);
+    }
+    if ((rc = build_tables(s, cmask))) return rc;
+    const RankTables& tb = s->tables;
+    const uint32_t R = tb.R;
+    uint32_t tau_init = R - 1;
+    if (thr_den) {  // largest rank whose fraction is <= thr_num / thr_den (rank 0 = distance 0 always qualifies)
+        uint32_t r = 0;
+        while (r + 1 < R && (uint64_t)tb.frac_h[r + 1] * thr_den <= (uint64_t)thr_num * tb.frac_n[r + 1]) r++;
+        tau_init = r;
+    }
+
+    // bootstrap plan (block units): round 0 accepts everything over r0 blocks, then ranges grow 8x
+    const uint32_t r0 = std::max<uint32_t>(1, (2 * k + kBlockRows - 1) / kBlockRows);
+    uint64_t C64 = (uint64_t)r0 * kBlockRows + 40ull * k + 2048;
+    C64 = (C64 + 1023) / 1024 * 1024;
+    const uint32_t C = (uint32_t)std::min<uint64_t>(C64, 1u << 26);
+
+    // tile size from a scratch budget
+    const size_t per_query = (size_t)C * 8 + (size_t)R * 4 + 64;
+    const size_t budget = (size_t)6 << 30;
+    uint32_t tile_max = (uint32_t)std::max<size_t>(1, std::min<size_t>(kMaxTile, budget / per_query));
+    tile_max = std::min<uint32_t>(tile_max, (uint32_t)Q);
+
+    if (s->d_queries.ensure(Q * 32) || s->d_qmap.ensure(Q * 4) || s->d_tau.ensure((size_t)tile_max * 4) ||
+        s->d_hist.ensure((size_t)tile_max * R * 4) || s->d_cnt.ensure((size_t)tile_max * 4) ||
+        s->d_ovf.ensure((size_t)tile_max * 4) || s->d_cand.ensure((size_t)tile_max * C * 8) ||
+        s->d_fb.ensure((size_t)tile_max * 8) || s->h_flags.ensure((size_t)tile_max * 16))
+        return ISX_ECUDA;
+
+    // queries in group order on the device + the map back to original positions
+    if (s->h_qmap.ensure(Q * 4)) return ISX_ECUDA;
+    memcpy(s->h_qmap.p, order.data(), Q * 4);
+    CU(cudaMemcpyAsync(s->d_qmap.p, s->h_qmap.p, Q * 4, cudaMemcpyHostToDevice, s->stream));
+    if (!q_on_device) {
+        if (s->h_queries.ensure(Q * 32)) return ISX_ECUDA;
+        uint8_t* hq = s->h_queries.as<uint8_t>();
+        for (size_t i = 0; i < Q; i++) {
+            const uint8_t* src = queries + (size_t)order[i] * 32;
+            uint32_t L = qlens[order[i]];
+            memcpy(hq + i * 32, src, L);
+            memset(hq + i * 32 + L, 0, 32 - L);
+        }
+        CU(cudaMemcpyAsync(s->d_queries.p, hq, Q * 32, cudaMemcpyHostToDevice, s->stream));
+    } else {
+        // device queries: gather rows into group order with plain 32-byte copies per run of equal order
+        size_t i = 0;
+        while (i < Q) {
+            size_t j = i + 1;
+            while (j < Q && order[j] == order[j - 1] + 1) j++;
+            CU(cudaMemcpyAsync(s->d_queries.as<uint8_t>() + i * 32, queries + (size_t)order[i] * 32, (j - i) * 32,
+                               cudaMemcpyDeviceToDevice, s->stream));
+            i = j;
+        }
+    }
+
+    if (s->profiling) CU(cudaEventRecord(s->ev[0], s->stream));
+    const uint32_t sort_cap = std::min<uint32_t>(cap_max, std::max<uint32_t>(1024, [&] { uint32_t c = 1024; while (c < 4 * k && c < cap_max) c *= 2; return c; }()));
+    const size_t sel_smem = select_smem(sort_cap, key_words);
+    {
+        cudaFuncAttributes fa;
+        CU(cudaFuncGetAttributes(&fa, k_select));
+        CU(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem_optin - (int)fa.sharedSizeBytes));
+    }
+
+    size_t g0 = 0;
+    while (g0 < Q) {
+        const uint32_t Lq = qlens[order[g0]];
+        size_t g1 = g0;
+        while (g1 < Q && qlens[order[g1]] == Lq) g1++;
+        for (size_t t0 = g0; t0 < g1; t0 += tile_max) {
+            const uint32_t T = (uint32_t)std::min<size_t>(tile_max, g1 - t0);
+            st.passes++;
+            ScanParams p{};
+            p.segs = s->d_segs.as<SegDesc>();
+            p.blocks = s->d_blocks.as<uint2>();
+            p.queries = s->d_queries.as<uint32_t>() + t0 * 8;
+            p.T = T;
+            p.qlen_bytes = Lq;
+            p.tau = s->d_tau.as<uint32_t>();
+            p.hist = s->d_hist.as<uint32_t>();
+            p.cand_cnt = s->d_cnt.as<uint32_t>();
+            p.cand = s->d_cand.as<uint64_t>();
+            p.overflow = s->d_ovf.as<uint32_t>();
+            p.C = C; p.R = R; p.k = k;
+            p.rank_tab = tb.d_rank.as<uint16_t>();
+            p.hmax_tab = tb.d_hmax.as<uint16_t>();
+            p.update_tau = 1;
+
+            {
+                size_t total = (size_t)T * R;
+                uint32_t grid = (uint32_t)std::min<size_t>((total + 255) / 256, (size_t)s->sm_count * 8);
+                grid = std::max<uint32_t>(grid, (T + 255) / 256);
+                k_init_queries<<<grid, 256, 0, s->stream>>>(p.tau, p.hist, p.cand_cnt, p.overflow, T, R, tau_init);
+                CU(cudaGetLastError());
+                st.kernel_launches++;
+            }
+            if (s->profiling) CU(cudaEventRecord(s->ev[1], s->stream));
+            // bootstrap rounds, then the bulk
+            const uint32_t wave_blocks = (uint32_t)s->sm_count * 4 * 4;  // ~ one wave of the main launch
+            uint32_t done = 0, span = r0;
+            const uint32_t bpi_main = T >= 64 ? 4 : (T >= 8 ? 8 : 16);
+            while (done < n_blocks_total) {
+                uint32_t remaining = n_blocks_total - done;
+                bool last = (span * 8 >= wave_blocks * 2) || (span >= remaining);
+                uint32_t take = last ? remaining : std::min(span, remaining);
+                if ((rc = scan_range(s, p, done, done + take, last ? bpi_main : 1))) return rc;
+                done += take;
+                span *= 8;
+            }
+            if (s->profiling) CU(cudaEventRecord(s->ev[2], s->stream));
+
+            SelectParams sp{};
+            sp.segs = p.segs; sp.hist = p.hist; sp.cand_cnt = p.cand_cnt; sp.cand = p.cand; sp.overflow = p.overflow;
+            sp.qmap = s->d_qmap.as<uint32_t>() + t0;
+            sp.C = C; sp.R = R; sp.k = k; sp.T = T; sp.qlen_bytes = Lq; sp.sort_cap = sort_cap; sp.key_words = key_words;
+            sp.tau_init = tau_init;
+            sp.out_khi = out.khi; sp.out_klo = out.klo; sp.out_h = out.h; sp.out_n = out.n; sp.out_cnt = out.cnt;
+            sp.out_codes = out.codes;
+            sp.fallback_info = s->d_fb.as<uint32_t>();
+            sp.skip_overflowed = 1;
+            k_select<<<T, kSelectThreads, sel_smem, s->stream>>>(sp);
+            CU(cudaGetLastError());
+            st.kernel_launches++;
+            if (s->profiling) CU(cudaEventRecord(s->ev[3], s->stream));
+
+            // overflow flags + candidate counts back to the host (tiny)
+            uint32_t* hf = s->h_flags.as<uint32_t>();
+            CU(cudaMemcpyAsync(hf, p.overflow, (size_t)T * 4, cudaMemcpyDeviceToHost, s->stream));
+            CU(cudaMemcpyAsync(hf + T, p.cand_cnt, (size_t)T * 4, cudaMemcpyDeviceToHost, s->stream));
+            CU(cudaStreamSynchronize(s->stream));
+            if (s->profiling) {
+                float a = 0, b = 0;
+                CU(cudaEventElapsedTime(&a, s->ev[1], s->ev[2]));
+                CU(cudaEventElapsedTime(&b, s->ev[2], s->ev[3]));
+                st.scan_ms += a;
+                st.select_ms += b;
+            }
+            std::vector<uint32_t> fb;
+            for (uint32_t i = 0; i < T; i++) {
+                st.candidates += hf[T + i];
+                if (hf[i]) fb.push_back(i);
+            }
+            if (!fb.empty()) {
+                // exact re-scan of the overflowed queries, one at a time: the histogram is still exact,
+                // so d* and the number of rows with rank <= d* are known; collect exactly those rows.
+                CU(cudaMemcpyAsync(hf + 2 * T, s->d_fb.p, (size_t)T * 8, cudaMemcpyDeviceToHost, s->stream));
+                CU(cudaStreamSynchronize(s->stream));
+                std::vector<uint32_t> info(hf + 2 * T, hf + 2 * T + 2 * T);
+                for (uint32_t qi : fb) {
+                    st.fallback_queries++;
+                    uint32_t dstar = info[2 * qi], count_le = info[2 * qi + 1];
+                    size_t C2 = (size_t)count_le + 1024;
+                    if (s->d_fb_cand.ensure(C2 * 8)) return ISX_ENOMEM;
+                    ScanParams p2 = p;
+                    p2.queries = p.queries + (size_t)qi * 8;
+                    p2.T = 1;
+                    // state block of query 0 of the tile is free to reuse now (its results are written)
+                    p2.cand = s->d_fb_cand.as<uint64_t>();
+                    p2.C = (uint32_t)std::min<size_t>(C2, 0xffffffffu);
+                    p2.update_tau = 0;
+                    k_init_queries<<<std::max<uint32_t>(1, (R + 255) / 256), 256, 0, s->stream>>>(p2.tau, p2.hist, p2.cand_cnt, p2.overflow, 1, R, dstar);
+                    CU(cudaGetLastError());
+                    st.kernel_launches++;
+                    if ((rc = scan_range(s, p2, 0, n_blocks_total, 16))) return rc;
+                    SelectParams sp2 = sp;
+                    sp2.cand = p2.cand; sp2.C = p2.C; sp2.T = 1; sp2.qmap = sp.qmap + qi; sp2.tau_init = dstar;
+                    sp2.skip_overflowed = 0;
+                    k_select<<<1, kSelectThreads, sel_smem, s->stream>>>(sp2);
+                    CU(cudaGetLastError());
+                    st.kernel_launches++;
+                    CU(cudaStreamSynchronize(s->stream));
+                    // NOTE: the tile's own state of slot 0 was clobbered, which is fine: the tile is finished.
+                }
+            }
+        }
+        g0 = g1;
+    }
+    if (s->profiling) {
+        CU(cudaStreamSynchronize(s->stream));
+        float t = 0;
+        CU(cudaEventElapsedTime(&t, s->ev[0], s->ev[3]));
+        st.total_ms = t;
+    }
+    return 0;
+}
+
+}  // namespace isx
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* isx_last_error(void) { return g_err.c_str(); }
+int isx_abi_version(void) { return ISX_ABI_VERSION; }
+
+int isx_device_count(int* n_out) {
+    if (!n_out) return fail(ISX_EINVAL, "n_out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *n_out = 0; return fail(ISX_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    *n_out = n;
+    return 0;
+}
+
+int isx_open(isx_store_t** out, int device, uint32_t key_bytes, uint32_t max_bytes, uint32_t fixed_len) {
+    if (!out) return fail(ISX_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (key_bytes != 8 && key_bytes != 16) return fail(ISX_EINVAL, "key_bytes must be 8 or 16, got %u", key_bytes);
+    if (max_bytes < 1 || max_bytes > ISX_MAX_BYTES) return fail(ISX_EINVAL, "max_bytes must be 1..32, got %u", max_bytes);
+    if (fixed_len > max_bytes) return fail(ISX_EINVAL, "fixed_len %u exceeds max_bytes %u", fixed_len, max_bytes);
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(ISX_ECUDA, "no CUDA device available (%s) - this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+    if (device < 0 || device >= n) return fail(ISX_EINVAL, "device %d out of range (have %d)", device, n);
+    CU(cudaSetDevice(device));
+    isx_store* s = new (std::nothrow) isx_store();
+    if (!s) return fail(ISX_ENOMEM, "out of host memory");
+    s->device = device;
+    s->key_bytes = key_bytes;
+    s->max_bytes = max_bytes;
+    s->fixed_len = fixed_len;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete s; return fail(ISX_ECUDA, "cudaGetDeviceProperties failed"); }
+    if (prop.major < 10) { delete s; return fail(ISX_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor); }
+    s->sm_count = prop.multiProcessorCount;
+    s->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete s; return fail(ISX_ECUDA, "cudaStreamCreate failed"); }
+    s->stream = s->own_stream;
+    for (auto& ev : s->ev)
+        if (cudaEventCreate(&ev) != cudaSuccess) { delete s; return fail(ISX_ECUDA, "cudaEventCreate failed"); }
+    *out = s;
+    return 0;
+}
+
+static void free_rows(isx_store* s) {
+    for (auto& sg : s->segs) if (sg.d_mem) cudaFree(sg.d_mem);
+    s->segs.clear();
+    for (auto& v : s->bucket_segs) v.clear();
+    memset(s->bucket_rows, 0, sizeof s->bucket_rows);
+    s->device_bytes = 0;
+    s->map.clear();
+    s->segs_dirty = true;
+    s->version++;
+}
+
+int isx_close(isx_store_t* s) {
+    if (!s) return 0;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    free_rows(s);
+    DevBuf* bufs[] = {&s->d_segs, &s->d_blocks, &s->tables.d_rank, &s->tables.d_hmax, &s->d_stage_codes, &s->d_stage_keys,
+                      &s->d_stage_dest, &s->d_moves, &s->d_queries, &s->d_tau, &s->d_hist, &s->d_cnt, &s->d_ovf, &s->d_cand,
+                      &s->d_qmap, &s->d_fb, &s->d_fb_cand, &s->d_out_khi, &s->d_out_klo, &s->d_out_h, &s->d_out_n,
+                      &s->d_out_cnt, &s->d_out_codes};
+    for (DevBuf* b : bufs) b->release();
+    PinnedBuf* pbufs[] = {&s->h_queries, &s->h_qmap, &s->h_flags, &s->h_out};
+    for (PinnedBuf* b : pbufs) b->release();
+    for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    delete s;
+    return 0;
+}
+
+int isx_set_stream(isx_store_t* s, void* cuda_stream) {
+    if (!s) return fail(ISX_EINVAL, "store is NULL");
+    std::lock_guard<std::mutex> g(s->work_mu);
+    s->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : s->own_stream;
+    return 0;
+}
+
+int isx_set_profiling(isx_store_t* s, int enabled) {
+    if (!s) return fail(ISX_EINVAL, "store is NULL");
+    s->profiling = enabled != 0;
+    return 0;
+}
+
+int isx_get_stats(isx_store_t* s, isx_stats_t* out) {
+    if (!s || !out) return fail(ISX_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> g(s->work_mu);
+    *out = s->stats;
+    return 0;
+}
+
+int isx_size(isx_store_t* s, uint64_t* n_out) {
+    if (!s || !n_out) return fail(ISX_EINVAL, "NULL argument");
+    std::shared_lock<std::shared_mutex> g(s->rows_mu);
+    *n_out = s->map.size();
+    return 0;
+}
+
+int isx_device_bytes(isx_store_t* s, uint64_t* n_out) {
+    if (!s || !n_out) return fail(ISX_EINVAL, "NULL argument");
+    std::shared_lock<std::shared_mutex> g(s->rows_mu);
+    *n_out = s->device_bytes;
+    return 0;
+}
+
+int isx_length_mask(isx_store_t* s, uint32_t* mask_out) {
+    if (!s || !mask_out) return fail(ISX_EINVAL, "NULL argument");
+    std::shared_lock<std::shared_mutex> g(s->rows_mu);
+    uint32_t m = 0;
+    for (uint32_t L = 1; L <= kMaxBytes; L++) if (s->bucket_rows[L]) m |= 1u << (L - 1);
+    *mask_out = m;
+    return 0;
+}
+
+int isx_max_k(isx_store_t* s, uint32_t* k_out) {
+    if (!s || !k_out) return fail(ISX_EINVAL, "NULL argument");
+    *k_out = max_sort_cap(s);
+    return 0;
+}
+
+int isx_clear(isx_store_t* s) {
+    if (!s) return fail(ISX_EINVAL, "store is NULL");
+    std::unique_lock<std::shared_mutex> g(s->rows_mu);
+    int rc = set_device(s);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    free_rows(s);
+    return 0;
+}
+
+int isx_add(isx_store_t* s, const void* keys, const uint8_t* codes, const uint8_t* lens, size_t n, uint8_t* added) {
+    if (!s) return fail(ISX_EINVAL, "store is NULL");
+    if (n == 0) return 0;
+    if (!keys || !codes || !lens) return fail(ISX_EINVAL, "NULL input array");
+    std::unique_lock<std::shared_mutex> g(s->rows_mu);
+    std::lock_guard<std::mutex> gw(s->work_mu);
+    int rc = set_device(s);
+    if (rc) return rc;
+    for (size_t i = 0; i < n; i++) {
+        uint32_t L = lens[i];
+        if (L < 1 || L > s->max_bytes) return fail(ISX_EINVAL, "row %zu: code length %u bytes outside 1..%u", i, L, s->max_bytes);
+        if (s->fixed_len && L != s->fixed_len) return fail(ISX_EINVAL, "row %zu: code length %u bytes, index expects %u", i, L, s->fixed_len);
+    }
+    s->map.reserve(s->map.size() + n);
+    // rows needed per bucket (upper bound: duplicates are skipped later) so big batches get big segments
+    uint64_t need[kMaxBytes + 1] = {0};
+    for (size_t i = 0; i < n; i++) need[lens[i]]++;
+
+    std::vector<uint64_t> dest(n, ~0ull);
+    const size_t PF = 16;
+    for (size_t i = 0; i < std::min(n, PF); i++) s->map.prefetch(load_key(s, keys, i));
+    size_t n_added = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (i + PF < n) s->map.prefetch(load_key(s, keys, i + PF));
+        Key128 key = load_key(s, keys, i);
+        uint32_t L = lens[i];
+        uint64_t dummy;
+        if (s->map.find(key, &dummy)) { if (added) added[i] = 0; need[L]--; continue; }
+        // segment with room in bucket L
+        auto& bs = s->bucket_segs[L];
+        if (bs.empty() || s->segs[bs.back()].desc.n == s->segs[bs.back()].desc.cap) {
+            uint32_t grow = bs.empty() ? kMinSegRows : std::min<uint64_t>((uint64_t)s->segs[bs.back()].desc.cap * 4, kMaxSegRows);
+            uint64_t want = std::max<uint64_t>(grow, std::min<uint64_t>(need[L], kMaxSegRows));
+            uint32_t cap = (uint32_t)((want + kMinSegRows - 1) / kMinSegRows * kMinSegRows);
+            if ((rc = new_segment(s, L, cap))) return rc;
+        }
+        uint32_t sid = bs.back();
+        Segment& sg = s->segs[sid];
+        uint32_t row = sg.desc.n++;
+        sg.h_khi[row] = key.hi;
+        if (s->key_bytes == 16) sg.h_klo[row] = key.lo;
+        uint64_t loc = ((uint64_t)sid << 32) | row;
+        s->map.insert(key, loc);
+        dest[i] = loc;
+        s->bucket_rows[L]++;
+        need[L]--;
+        if (added) added[i] = 1;
+        n_added++;
+    }
+    if (n_added == 0) return 0;
+    s->segs_dirty = true;
+    s->version++;
+    if ((rc = upload_segs(s))) return rc;
+    // stage + scatter in chunks (bounded staging memory)
+    const size_t CH = (size_t)4 << 20;
+    for (size_t c0 = 0; c0 < n; c0 += CH) {
+        size_t cn = std::min(CH, n - c0);
+        if (s->d_stage_codes.ensure(cn * 32) || s->d_stage_keys.ensure(cn * s->key_bytes) || s->d_stage_dest.ensure(cn * 8)) return ISX_ENOMEM;
+        CU(cudaMemcpyAsync(s->d_stage_codes.p, codes + c0 * 32, cn * 32, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(s->d_stage_keys.p, reinterpret_cast<const uint8_t*>(keys) + c0 * s->key_bytes, cn * s->key_bytes, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(s->d_stage_dest.p, dest.data() + c0, cn * 8, cudaMemcpyHostToDevice, s->stream));
+        k_scatter_rows<<<(unsigned)((cn + 255) / 256), 256, 0, s->stream>>>(s->d_segs.as<SegDesc>(), s->d_stage_dest.as<uint64_t>(),
+                                                                            s->d_stage_codes.as<uint8_t>(), s->d_stage_keys.as<uint8_t>(),
+                                                                            s->key_bytes, cn);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    return 0;
+}
+
+int isx_remove(isx_store_t* s, const void* keys, size_t n, uint8_t* removed, uint64_t* n_removed) {
+    if (!s) return fail(ISX_EINVAL, "store is NULL");
+    if (n_removed) *n_removed = 0;
+    if (n == 0) return 0;
+    if (!keys) return fail(ISX_EINVAL, "NULL input array");
+    std::unique_lock<std::shared_mutex> g(s->rows_mu);
+    std::lock_guard<std::mutex> gw(s->work_mu);
+    int rc = set_device(s);
+    if (rc) return rc;
+    std::vector<uint4> moves;
+    uint64_t cnt = 0;
+    for (size_t i = 0; i < n; i++) {
+        Key128 key = load_key(s, keys, i);
+        uint64_t loc;
+        if (!s->map.find(key, &loc)) { if (removed) removed[i] = 0; continue; }
+        uint32_t sid = (uint32_t)(loc >> 32), row = (uint32_t)loc;
+        uint32_t L = s->segs[sid].len_bytes;
+        // last live row of the bucket
+        auto& bs = s->bucket_segs[L];
+        size_t li = bs.size();
+        while (li > 0 && s->segs[bs[li - 1]].desc.n == 0) li--;
+        uint32_t lsid = bs[li - 1];
+        Segment& last = s->segs[lsid];
+        uint32_t lrow = last.desc.n - 1;
+        s->map.erase(key);
+        if (!(lsid == sid && lrow == row)) {
+            Key128 moved{last.h_khi[lrow], s->key_bytes == 16 ? last.h_klo[lrow] : 0};
+            Segment& dst = s->segs[sid];
+            dst.h_khi[row] = moved.hi;
+            if (s->key_bytes == 16) dst.h_klo[row] = moved.lo;
+            s->map.update(moved, ((uint64_t)sid << 32) | row);
+            moves.push_back(make_uint4(sid, row, lsid, lrow));
+        }
+        last.desc.n--;
+        s->bucket_rows[L]--;
+        if (removed) removed[i] = 1;
+        cnt++;
+    }
+    if (n_removed) *n_removed = cnt;
+    if (cnt == 0) return 0;
+    s->segs_dirty = true;
+    s->version++;
+    if ((rc = upload_segs(s))) return rc;
+    if (!moves.empty()) {
+        if (s->d_moves.ensure(moves.size() * sizeof(uint4))) return ISX_ENOMEM;
+        CU(cudaMemcpyAsync(s->d_moves.p, moves.data(), moves.size() * sizeof(uint4), cudaMemcpyHostToDevice, s->stream));
+        k_move_rows<<<1, 32, 0, s->stream>>>(s->d_segs.as<SegDesc>(), s->d_moves.as<uint4>(), moves.size());
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    return 0;
+}
+
+int isx_contains(isx_store_t* s, const void* keys, size_t n, uint8_t* present) {
+    if (!s) return fail(ISX_EINVAL, "store is NULL");
+    if (n == 0) return 0;
+    if (!keys || !present) return fail(ISX_EINVAL, "NULL argument");
+    std::shared_lock<std::shared_mutex> g(s->rows_mu);
+    for (size_t i = 0; i < n; i++) {
+        uint64_t loc;
+        present[i] = s->map.find(load_key(s, keys, i), &loc) ? 1 : 0;
+    }
+    return 0;
+}
+
+int isx_get(isx_store_t* s, const void* keys, size_t n, uint8_t* codes_out, uint8_t* lens_out) {
+    if (!s) return fail(ISX_EINVAL, "store is NULL");
+    if (n == 0) return 0;
+    if (!keys || !codes_out || !lens_out) return fail(ISX_EINVAL, "NULL argument");
+    std::shared_lock<std::shared_mutex> g(s->rows_mu);
+    std::lock_guard<std::mutex> gw(s->work_mu);
+    int rc = set_device(s);
+    if (rc) return rc;
+    std::vector<uint64_t> loc(n, ~0ull);
+    size_t found = 0;
+    for (size_t i = 0; i < n; i++) {
+        uint64_t l;
+        if (s->map.find(load_key(s, keys, i), &l)) { loc[i] = l; lens_out[i] = (uint8_t)s->segs[(uint32_t)(l >> 32)].len_bytes; found++; }
+        else lens_out[i] = 0;
+    }
+    if (!found) { memset(codes_out, 0, n * 32); return 0; }
+    if ((rc = upload_segs(s))) return rc;
+    if (s->d_stage_dest.ensure(n * 8) || s->d_stage_codes.ensure(n * 32)) return ISX_ENOMEM;
+    CU(cudaMemcpyAsync(s->d_stage_dest.p, loc.data(), n * 8, cudaMemcpyHostToDevice, s->stream));
+    k_gather_rows<<<(unsigned)((n * 8 + 255) / 256), 256, 0, s->stream>>>(s->d_segs.as<SegDesc>(), s->d_stage_dest.as<uint64_t>(),
+                                                                          s->d_stage_codes.as<uint8_t>(), n);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(codes_out, s->d_stage_codes.p, n * 32, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int isx_search(isx_store_t* s, const uint8_t* queries, const uint8_t* qlens, size_t q, uint32_t k, uint32_t thr_num,
+               uint32_t thr_den, void* keys_out, uint16_t* hamming_out, uint16_t* nbits_out, uint32_t* counts_out,
+               uint8_t* codes_out) {
+    if (!s) return fail(ISX_EINVAL, "store is NULL");
+    if (k < 1) return fail(ISX_EINVAL, "`count` must be >= 1");
+    if (q == 0) return 0;
+    if (!queries || !qlens || !keys_out || !hamming_out || !nbits_out || !counts_out) return fail(ISX_EINVAL, "NULL argument");
+    std::shared_lock<std::shared_mutex> g(s->rows_mu);
+    std::lock_guard<std::mutex> gw(s->work_mu);
+    int rc = set_device(s);
+    if (rc) return rc;
+    size_t qk = q * (size_t)k;
+    if (s->d_out_khi.ensure(qk * 8) || s->d_out_klo.ensure(qk * 8) || s->d_out_h.ensure(qk * 2) || s->d_out_n.ensure(qk * 2) ||
+        s->d_out_cnt.ensure(q * 4) || (codes_out && s->d_out_codes.ensure(qk * 32)))
+        return ISX_ENOMEM;
+    SearchOut out{s->d_out_khi.as<uint64_t>(), s->d_out_klo.as<uint64_t>(), s->d_out_h.as<uint16_t>(), s->d_out_n.as<uint16_t>(),
+                  s->d_out_cnt.as<uint32_t>(), codes_out ? s->d_out_codes.as<uint8_t>() : nullptr};
+    if ((rc = search_core(s, queries, false, qlens, q, k, thr_num, thr_den, out))) return rc;
+    // results -> pinned staging -> caller
+    size_t bytes = qk * (8 + 8 + 2 + 2) + q * 4;
+    if (s->h_out.ensure(bytes)) return ISX_ENOMEM;
+    uint8_t* h = s->h_out.as<uint8_t>();
+    uint64_t* h_khi = reinterpret_cast<uint64_t*>(h);
+    uint64_t* h_klo = h_khi + qk;
+    uint16_t* h_h = reinterpret_cast<uint16_t*>(h_klo + qk);
+    uint16_t* h_n = h_h + qk;
+    uint32_t* h_cnt = reinterpret_cast<uint32_t*>(h_n + qk);
+    CU(cudaMemcpyAsync(h_khi, out.khi, qk * 8, cudaMemcpyDeviceToHost, s->stream));
+    if (s->key_bytes == 16) CU(cudaMemcpyAsync(h_klo, out.klo, qk * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(h_h, out.h, qk * 2, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(h_n, out.n, qk * 2, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(h_cnt, out.cnt, q * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (codes_out) CU(cudaMemcpyAsync(codes_out, out.codes, qk * 32, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    memcpy(hamming_out, h_h, qk * 2);
+    memcpy(nbits_out, h_n, qk * 2);
+    memcpy(counts_out, h_cnt, q * 4);
+    if (s->key_bytes == 8) memcpy(keys_out, h_khi, qk * 8);
+    else for (size_t i = 0; i < qk; i++) store_key(s, keys_out, i, h_khi[i], h_klo[i]);
+    return 0;
+}
+
+int isx_search_device(isx_store_t* s, const uint8_t* queries, int queries_on_device, const uint8_t* qlens, size_t q,
+                      uint32_t k, uint32_t thr_num, uint32_t thr_den, uint64_t* d_keys_hi, uint64_t* d_keys_lo,
+                      uint16_t* d_hamming, uint16_t* d_nbits, uint32_t* d_counts, int sync) {
+    if (!s) return fail(ISX_EINVAL, "store is NULL");
+    if (k < 1) return fail(ISX_EINVAL, "`count` must be >= 1");
+    if (q == 0) return 0;
+    if (!queries || !qlens || !d_keys_hi || !d_keys_lo || !d_hamming || !d_nbits || !d_counts) return fail(ISX_EINVAL, "NULL argument");
+    std::shared_lock<std::shared_mutex> g(s->rows_mu);
+    std::lock_guard<std::mutex> gw(s->work_mu);
+    int rc = set_device(s);
+    if (rc) return rc;
+    SearchOut out{d_keys_hi, d_keys_lo, d_hamming, d_nbits, d_counts, nullptr};
+    if ((rc = search_core(s, queries, queries_on_device != 0, qlens, q, k, thr_num, thr_den, out))) return rc;
+    if (sync) CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int isx_merge_device(isx_store_t* s, uint32_t n_shards, size_t q, uint32_t k, const uint64_t* d_keys_hi,
+                     const uint64_t* d_keys_lo, const uint16_t* d_hamming, const uint16_t* d_nbits,
+                     const uint32_t* d_counts, uint64_t* d_out_keys_hi, uint64_t* d_out_keys_lo,
+                     uint16_t* d_out_hamming, uint16_t* d_out_nbits, uint32_t* d_out_counts, int sync) {
+    if (!s) return fail(ISX_EINVAL, "store is NULL");
+    if (q == 0) return 0;
+    if (n_shards < 1 || k < 1) return fail(ISX_EINVAL, "n_shards and k must be >= 1");
+    std::lock_guard<std::mutex> gw(s->work_mu);
+    int rc = set_device(s);
+    if (rc) return rc;
+    k_merge<<<(unsigned)q, 256, 0, s->stream>>>(n_shards, (uint32_t)q, k, d_keys_hi, d_keys_lo, d_hamming, d_nbits, d_counts,
+                                               d_out_keys_hi, d_out_keys_lo, d_out_hamming, d_out_nbits, d_out_counts);
+    CU(cudaGetLastError());
+    s->stats.kernel_launches++;
+    if (sync) CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+// ---- snapshot ----------------------------------------------------------------------------------
+// magic | key_bytes, max_bytes, fixed_len, 0 | total rows | per bucket: [u32 L][u64 rows] then chunks
+// [u32 n][keys hi n*8][keys lo n*8 if 16-byte keys][codes n*L] ... [u32 0] | [u32 0] end marker
+static const char kMagic[8] = {'I', 'S', 'X', 'B', '2', '0', '0', '1'};
+
+int isx_save(isx_store_t* s, const char* path) {
+    if (!s || !path) return fail(ISX_EINVAL, "NULL argument");
+    std::shared_lock<std::shared_mutex> g(s->rows_mu);
+    std::lock_guard<std::mutex> gw(s->work_mu);
+    int rc = set_device(s);
+    if (rc) return rc;
+    std::string tmp = std::string(path) + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return fail(ISX_EIO, "cannot open %s for writing", tmp.c_str());
+    bool ok = true;
+    auto W = [&](const void* p, size_t n) { if (ok && n && fwrite(p, 1, n, f) != n) ok = false; };
+    uint32_t hdr[4] = {s->key_bytes, s->max_bytes, s->fixed_len, 0};
+    uint64_t total = s->map.size();
+    W(kMagic, 8); W(hdr, sizeof hdr); W(&total, 8);
+    std::vector<uint32_t> plane;
+    std::vector<uint8_t> rows;
+    const uint32_t zero = 0;
+    for (uint32_t L = 1; L <= kMaxBytes && ok; L++) {
+        uint64_t n = s->bucket_rows[L];
+        if (!n) continue;
+        uint32_t L32 = L;
+        W(&L32, 4); W(&n, 8);
+        uint32_t words = (L + 3) / 4;
+        for (uint32_t sid : s->bucket_segs[L]) {
+            Segment& sg = s->segs[sid];
+            uint32_t sn = sg.desc.n;
+            if (!sn) continue;
+            W(&sn, 4);
+            W(sg.h_khi.data(), (size_t)sn * 8);
+            if (s->key_bytes == 16) W(sg.h_klo.data(), (size_t)sn * 8);
+            plane.resize((size_t)words * sn);
+            for (uint32_t w = 0; w < words; w++) {
+                cudaError_t e = cudaMemcpyAsync(plane.data() + (size_t)w * sn, sg.desc.planes + (size_t)w * sg.desc.cap, (size_t)sn * 4,
+                                                cudaMemcpyDeviceToHost, s->stream);
+                if (e != cudaSuccess) { fclose(f); remove(tmp.c_str()); return fail(ISX_ECUDA, "snapshot copy failed: %s", cudaGetErrorString(e)); }
+            }
+            if (cudaStreamSynchronize(s->stream) != cudaSuccess) { fclose(f); remove(tmp.c_str()); return fail(ISX_ECUDA, "snapshot copy failed"); }
+            rows.resize((size_t)sn * L);
+            for (uint32_t r = 0; r < sn; r++) {
+                uint8_t tmpb[32];
+                for (uint32_t w = 0; w < words; w++) memcpy(tmpb + 4 * w, &plane[(size_t)w * sn + r], 4);
+                memcpy(&rows[(size_t)r * L], tmpb, L);
+            }
+            W(rows.data(), rows.size());
+        }
+        W(&zero, 4);
+    }
+    W(&zero, 4);
+    if (fclose(f) != 0) ok = false;
+    if (!ok) { remove(tmp.c_str()); return fail(ISX_EIO, "write to %s failed", tmp.c_str()); }
+    if (rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); return fail(ISX_EIO, "rename to %s failed", path); }
+    return 0;
+}
+
+int isx_load(isx_store_t* s, const char* path) {
+    if (!s || !path) return fail(ISX_EINVAL, "NULL argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(ISX_EIO, "cannot open %s", path);
+    char magic[8];
+    uint32_t hdr[4];
+    uint64_t total;
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, kMagic, 8) != 0 || fread(hdr, 1, sizeof hdr, f) != sizeof hdr || fread(&total, 1, 8, f) != 8) {
+        fclose(f);
+        return fail(ISX_EIO, "%s is not an isx snapshot", path);
+    }
+    if (hdr[0] != s->key_bytes || hdr[1] > s->max_bytes || hdr[2] != s->fixed_len) {
+        fclose(f);
+        return fail(ISX_EINVAL, "snapshot %s was written for key_bytes=%u max_bytes=%u fixed_len=%u", path, hdr[0], hdr[1], hdr[2]);
+    }
+    int rc = isx_clear(s);
+    if (rc) { fclose(f); return rc; }
+    std::vector<uint64_t> khi, klo;
+    std::vector<uint8_t> keys, rows, codes, lens;
+    auto bad = [&](const char* why) { fclose(f); isx_clear(s); return fail(ISX_EIO, "%s snapshot %s", why, path); };
+    for (;;) {
+        uint32_t L;
+        uint64_t n;
+        if (fread(&L, 1, 4, f) != 4) return bad("truncated");
+        if (L == 0) break;
+        if (L > kMaxBytes || fread(&n, 1, 8, f) != 8) return bad("corrupt");
+        for (;;) {
+            uint32_t sn;
+            if (fread(&sn, 1, 4, f) != 4) return bad("truncated");
+            if (sn == 0) break;
+            if (sn > kMaxSegRows) return bad("corrupt");
+            khi.resize(sn);
+            if (fread(khi.data(), 8, sn, f) != sn) return bad("truncated");
+            if (s->key_bytes == 16) { klo.resize(sn); if (fread(klo.data(), 8, sn, f) != sn) return bad("truncated"); }
+            rows.resize((size_t)sn * L);
+            if (fread(rows.data(), 1, rows.size(), f) != rows.size()) return bad("truncated");
+            codes.assign((size_t)sn * 32, 0);
+            lens.assign(sn, (uint8_t)L);
+            for (uint32_t r = 0; r < sn; r++) memcpy(&codes[(size_t)r * 32], &rows[(size_t)r * L], L);
+            const void* kp = khi.data();
+            if (s->key_bytes == 16) {
+                keys.resize((size_t)sn * 16);
+                for (uint32_t r = 0; r < sn; r++) store_key(s, keys.data(), r, khi[r], klo[r]);
+                kp = keys.data();
+            }
+            if ((rc = isx_add(s, kp, codes.data(), lens.data(), sn, nullptr))) { fclose(f); return rc; }
+        }
+    }
+    fclose(f);
+    uint64_t have = 0;
+    isx_size(s, &have);
+    if (have != total) return fail(ISX_EIO, "snapshot %s: expected %llu rows, loaded %llu", path, (unsigned long long)total, (unsigned long long)have);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,568 @@
+// kernels.cuh - sm_100a kernels of the exact NPHD / Hamming top-k path.
+//
+// Replaces the native metric + exact scan of `usearch-iscc` behind
+//   /root/reference/iscc_search/indexes/usearch/index.py:2037           (ShardedNphdIndex.search)
+//   /root/reference/iscc_search/indexes/simprint/usearch_core.py:165    (ShardedIndex128.search)
+// Formula: NPHD(a,b) = popc(a[:m]^b[:m]) / (8m), m = min(len) bytes
+//   (/root/reference/docs/explanation/similarity-search.md:24-32).
+//
+// Data layout in HBM: per code length L a bucket of segments; a segment holds
+// `cap` rows as 32-bit WORD PLANES plane[w][row], w < ceil(L/4), so a query that shares only m
+// bytes with the bucket streams just the first ceil(m/4) planes, each with perfectly coalesced
+// 128-bit loads (4 rows per LDG.128). Keys live in separate arrays touched only for winners.
+//
+// Selection is an exact counting select on the tiny integer distance domain: every (m, h) pair is
+// mapped to the dense rank of the rational h/(8m); per query a global histogram over ranks plus
+// a running rank threshold tau (always >= the true k-th rank) decides which rows are emitted as
+// candidates; the final kernel cuts at the exact k-th rank and breaks ties by key.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace isx {
+
+constexpr int kMaxBytes = 32;
+constexpr int kThreads = 256;          // scan CTA
+constexpr int kRowsPerStep = kThreads * 4;  // one LDG.128 per plane per thread = 4 rows
+constexpr int kMaxTile = 2048;         // queries resident in shared memory per launch
+constexpr int kSelectThreads = 1024;
+constexpr uint32_t kRowBits = 22;      // rows per segment <= 4 Mi
+constexpr uint32_t kSegBits = 16;      // segments per store <= 65536
+constexpr uint32_t kHBits = 9;         // hamming <= 256
+constexpr uint32_t kRankBits = 13;     // dense ranks < 8192
+
+struct SegDesc {
+    uint32_t* planes;   // [words][cap]
+    uint64_t* khi;      // [cap]
+    uint64_t* klo;      // [cap] or nullptr (8-byte keys)
+    uint32_t cap;       // allocated rows (multiple of 4096)
+    uint32_t n;         // live rows
+    uint32_t len_bytes; // code length of the bucket
+    uint32_t words;     // ceil(len_bytes / 4)
+};
+
+struct ScanParams {
+    const SegDesc* segs;
+    const uint2* blocks;         // (segment id, first row) of every live 1024-row block, bucket order
+    uint32_t block_begin, block_end;  // this launch: blocks of ONE bucket (uniform m / WE)
+    uint32_t blocks_per_item;    // consecutive blocks a CTA takes per work item (multiple of G)
+    const uint32_t* queries;     // [T][8] words, little-endian words of the zero padded code
+    uint32_t T;                  // queries in this launch (<= kMaxTile)
+    uint32_t qlen_bytes;         // length of every query of this launch
+    uint32_t* tau;               // [T] running rank threshold
+    uint32_t* hist;              // [T][R]
+    uint32_t* cand_cnt;          // [T]
+    uint64_t* cand;              // [T][C]
+    uint32_t* overflow;          // [T]
+    uint32_t C, R, k;
+    const uint16_t* rank_tab;    // [33][257]: rank of h/(8m)
+    const uint16_t* hmax_tab;    // [33][R]:  max h with rank(m, h) <= r
+    uint32_t update_tau;         // 0: fixed threshold (exact re-scan)
+};
+
+__device__ __forceinline__ uint64_t pack_cand(uint32_t rank, uint32_t h, uint32_t seg, uint32_t row) {
+    return ((uint64_t)rank << (kHBits + kSegBits + kRowBits)) | ((uint64_t)h << (kSegBits + kRowBits)) |
+           ((uint64_t)seg << kRowBits) | row;
+}
+__device__ __forceinline__ uint32_t cand_rank(uint64_t c) { return (uint32_t)(c >> (kHBits + kSegBits + kRowBits)); }
+__device__ __forceinline__ uint32_t cand_h(uint64_t c) { return (uint32_t)(c >> (kSegBits + kRowBits)) & ((1u << kHBits) - 1); }
+__device__ __forceinline__ uint32_t cand_seg(uint64_t c) { return (uint32_t)(c >> kRowBits) & ((1u << kSegBits) - 1); }
+__device__ __forceinline__ uint32_t cand_row(uint64_t c) { return (uint32_t)c & ((1u << kRowBits) - 1); }
+
+__device__ __forceinline__ uint4 ldg_stream(const uint32_t* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// Rare path: a row passed the running threshold of query q.
+__device__ __noinline__ void emit_candidate(const ScanParams& p, uint32_t q, uint32_t m, uint32_t h, uint32_t seg,
+                                            uint32_t row, uint32_t seg_n, unsigned char* dirty) {
+    if (row >= seg_n) return;  // padding rows of the last group
+    uint32_t rank = p.rank_tab[m * 257 + h];
+    atomicAdd(&p.hist[(size_t)q * p.R + rank], 1u);
+    uint32_t slot = atomicAdd(&p.cand_cnt[q], 1u);
+    if (slot < p.C) p.cand[(size_t)q * p.C + slot] = pack_cand(rank, h, seg, row);
+    else p.overflow[q] = 1u;
+    dirty[q] = 1;
+}
+
+// Tighten tau[q] to the smallest rank t with (observed) sum_{r<=t} hist[q][r] >= k. Observed counts
+// only under-count, so t is always >= the true k-th rank. One warp per query.
+__device__ __forceinline__ void tighten_tau(const ScanParams& p, uint32_t q, uint32_t lane) {
+    uint32_t tcur = __ldcg(&p.tau[q]);
+    const uint32_t* hq = p.hist + (size_t)q * p.R;
+    uint32_t cum = 0;
+    for (uint32_t base = 0; base <= tcur; base += 32) {
+        uint32_t r = base + lane;
+        uint32_t v = (r <= tcur) ? __ldcg(&hq[r]) : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += t;
+        }
+        unsigned hit = __ballot_sync(0xffffffffu, cum + incl >= p.k);
+        if (hit) {
+            uint32_t t = base + (uint32_t)(__ffs(hit) - 1);
+            if (lane == 0 && t < tcur) atomicMin(&p.tau[q], t);
+            return;
+        }
+        cum += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+// WE: words compared per pair (1..8). G: groups of 4 rows a thread keeps in flight.
+template <int WE, int G>
+__global__ void __launch_bounds__(kThreads) k_scan(const __grid_constant__ ScanParams p) {
+    constexpr int QW = (WE <= 4) ? 4 : 8;  // query words kept per query in shared memory
+    extern __shared__ uint4 smem_raw[];
+    uint32_t* qw = reinterpret_cast<uint32_t*>(smem_raw);   // [T][QW]
+    uint32_t* hm = qw + (size_t)p.T * QW;                    // [T]
+    unsigned char* dirty = reinterpret_cast<unsigned char*>(hm + p.T);  // [T]
+    const uint32_t tid = threadIdx.x;
+    const uint32_t T = p.T;
+
+    for (uint32_t i = tid; i < T * QW; i += kThreads) {
+        uint32_t q = i / QW, w = i % QW;
+        qw[i] = (w < WE) ? p.queries[q * 8 + w] : 0u;
+    }
+    for (uint32_t q = tid; q < T; q += kThreads) dirty[q] = 0;
+
+    // every block of this launch belongs to one bucket: m, the last-word mask and the threshold row are uniform
+    const uint32_t seg_len = p.segs[p.blocks[p.block_begin].x].len_bytes;
+    const uint32_t m = min(p.qlen_bytes, seg_len);               // bytes compared
+    const uint32_t mask_last = (m & 3u) ? ((1u << (8u * (m & 3u))) - 1u) : 0xffffffffu;
+    const uint16_t* hrow = p.hmax_tab + (size_t)m * p.R;
+    const uint32_t n_blocks = p.block_end - p.block_begin;
+    const uint32_t n_items = (n_blocks + p.blocks_per_item - 1) / p.blocks_per_item;
+
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const uint32_t b_lo = p.block_begin + item * p.blocks_per_item;
+        const uint32_t b_hi = min(b_lo + p.blocks_per_item, p.block_end);
+        __syncthreads();  // previous item's readers of hm are done
+        for (uint32_t q = tid; q < T; q += kThreads) hm[q] = hrow[__ldcg(&p.tau[q])];
+        __syncthreads();
+
+        for (uint32_t b = b_lo; b < b_hi; b += G) {
+            uint4 a[G][WE];
+            uint32_t seg_id[G], row0[G], seg_n[G];
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const bool live = (b + g < b_hi);
+                const uint2 blk = p.blocks[live ? b + g : b];
+                const SegDesc* sd = p.segs + blk.x;
+                seg_id[g] = blk.x;
+                row0[g] = blk.y + tid * 4;
+                seg_n[g] = live ? sd->n : 0u;      // a dead group never emits
+                const uint32_t* base = sd->planes + row0[g];
+                const uint32_t cap = sd->cap;
+#pragma unroll
+                for (int w = 0; w < WE; w++) a[g][w] = ldg_stream(base + (size_t)w * cap);
+            }
+
+#pragma unroll 1
+            for (uint32_t q = 0; q < T; q++) {
+                uint32_t qv[WE];
+                {
+                    const uint4* qp = reinterpret_cast<const uint4*>(qw + (size_t)q * QW);
+                    uint4 v0 = qp[0];
+                    qv[0] = v0.x;
+                    if (WE > 1) qv[1] = v0.y;
+                    if (WE > 2) qv[2] = v0.z;
+                    if (WE > 3) qv[3] = v0.w;
+                    if (WE > 4) {
+                        uint4 v1 = qp[1];
+                        qv[4] = v1.x;
+                        if (WE > 5) qv[5] = v1.y;
+                        if (WE > 6) qv[6] = v1.z;
+                        if (WE > 7) qv[7] = v1.w;
+                    }
+                }
+                const uint32_t hmax = hm[q];
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+#pragma unroll
+                    for (int w = 0; w < WE; w++) {
+                        const uint32_t mk = (w == WE - 1) ? mask_last : 0xffffffffu;
+                        d0 += __popc((a[g][w].x ^ qv[w]) & mk);
+                        d1 += __popc((a[g][w].y ^ qv[w]) & mk);
+                        d2 += __popc((a[g][w].z ^ qv[w]) & mk);
+                        d3 += __popc((a[g][w].w ^ qv[w]) & mk);
+                    }
+                    uint32_t dmin = min(min(d0, d1), min(d2, d3));
+                    if (dmin <= hmax) {
+                        if (d0 <= hmax) emit_candidate(p, q, m, d0, seg_id[g], row0[g] + 0, seg_n[g], dirty);
+                        if (d1 <= hmax) emit_candidate(p, q, m, d1, seg_id[g], row0[g] + 1, seg_n[g], dirty);
+                        if (d2 <= hmax) emit_candidate(p, q, m, d2, seg_id[g], row0[g] + 2, seg_n[g], dirty);
+                        if (d3 <= hmax) emit_candidate(p, q, m, d3, seg_id[g], row0[g] + 3, seg_n[g], dirty);
+                    }
+                }
+            }
+        }
+
+        if (p.update_tau) {
+            __syncthreads();  // all emissions of this item are issued
+            __threadfence();
+            const uint32_t warp = tid >> 5, lane = tid & 31;
+            for (uint32_t q = warp; q < T; q += kThreads / 32) {
+                if (dirty[q]) {
+                    tighten_tau(p, q, lane);
+                    if (lane == 0) dirty[q] = 0;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-query state reset
+__global__ void k_init_queries(uint32_t* tau, uint32_t* hist, uint32_t* cand_cnt, uint32_t* overflow, uint32_t T,
+                               uint32_t R, uint32_t tau_init) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)T * R;
+    for (size_t j = i; j < total; j += (size_t)gridDim.x * blockDim.x) hist[j] = 0;
+    if (i < T) { tau[i] = tau_init; cand_cnt[i] = 0; overflow[i] = 0; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Final exact selection: one CTA per query.
+struct SelectParams {
+    const SegDesc* segs;
+    const uint32_t* hist;      // [T][R]
+    const uint32_t* cand_cnt;  // [T]
+    const uint64_t* cand;      // [T][C]  (or one big list when `single_list`)
+    const uint32_t* overflow;  // [T]
+    const uint32_t* qmap;      // [T] -> output row (original query index)
+    uint32_t C, R, k, T;
+    uint32_t qlen_bytes;
+    uint32_t sort_cap;         // entries that fit in shared memory
+    uint32_t key_words;        // 1 (uint64 keys) | 2 (128-bit keys)
+    uint32_t tau_init;         // threshold rank (R-1 = none)
+    uint64_t* out_khi; uint64_t* out_klo; uint16_t* out_h; uint16_t* out_n; uint32_t* out_cnt;
+    uint8_t* out_codes;        // optional [Q][k][32]
+    uint32_t* fallback_info;   // [T][2]: (needs fallback, count_le(d*)) for overflowed queries
+    uint32_t skip_overflowed;  // 1 in the normal pass; 0 in the fallback pass (lists are complete)
+};
+
+struct SortKey { uint32_t rank; uint64_t hi, lo; };
+__device__ __forceinline__ bool key_less(const SortKey& a, const SortKey& b) {
+    if (a.rank != b.rank) return a.rank < b.rank;
+    if (a.hi != b.hi) return a.hi < b.hi;
+    return a.lo < b.lo;
+}
+
+__global__ void __launch_bounds__(kSelectThreads) k_select(const SelectParams p) {
+    extern __shared__ uint4 smem_raw[];
+    // shared layout: khi[cap] | klo[cap] (if key_words==2) | rk[cap] | cidx[cap] | perm[cap] (u16 or u32)
+    const uint32_t cap = p.sort_cap;
+    uint64_t* s_khi = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* s_klo = s_khi + cap;
+    uint32_t* s_rk = reinterpret_cast<uint32_t*>(s_klo + (p.key_words == 2 ? cap : 0));
+    uint32_t* s_cidx = s_rk + cap;
+    uint32_t* s_perm = s_cidx + cap;
+    __shared__ uint32_t s_scan[kSelectThreads / 32];
+    __shared__ uint32_t s_dstar, s_count_lt, s_total_le, s_fill;
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_need;
+
+    const uint32_t q = blockIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t oq = p.qmap[q];
+    if (p.skip_overflowed && p.overflow[q]) {
+        // hist is still exact up to the final tau: report d* and count_le so the host can re-scan.
+        // (computed below, then we bail out before touching the truncated candidate list)
+    }
+    const uint32_t* hq = p.hist + (size_t)q * p.R;
+    const uint32_t n_list = min(p.cand_cnt[q], p.C);
+
+    // ---- 1. exact k-th rank d* from the histogram (block-wide scan over R bins) ----
+    if (tid == 0) { s_dstar = p.R; s_count_lt = 0; s_total_le = 0; s_fill = 0; }
+    __syncthreads();
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < p.R; base += kSelectThreads) {
+        uint32_t r = base + tid;
+        uint32_t v = (r < p.R && r <= p.tau_init) ? hq[r] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += t;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_scan[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= (uint32_t)o) w += t;
+            }
+            s_scan[lane] = w;  // inclusive warp totals
+        }
+        __syncthreads();
+        uint32_t before = carry + (warp ? s_scan[warp - 1] : 0u);
+        uint32_t cum_incl = before + incl;
+        uint32_t cum_excl = cum_incl - v;
+        if (r < p.R && cum_excl < p.k && cum_incl >= p.k) { s_dstar = r; s_count_lt = cum_excl; s_total_le = cum_incl; }
+        carry += s_scan[kSelectThreads / 32 - 1];
+        __syncthreads();
+        if (s_dstar != p.R) break;
+    }
+    __syncthreads();
+    if (s_dstar == p.R) {  // fewer than k rows within the threshold: take them all
+        if (tid == 0) { s_dstar = min(p.tau_init, p.R - 1); s_count_lt = carry; s_total_le = carry; }
+        __syncthreads();
+    }
+    const uint32_t dstar = s_dstar;
+    const uint32_t total_le = s_total_le;               // rows with rank <= d*
+    const uint32_t n_out = min(p.k, total_le);
+
+    if (p.skip_overflowed && p.overflow[q]) {
+        if (tid == 0) { p.fallback_info[2 * q] = dstar; p.fallback_info[2 * q + 1] = total_le; p.out_cnt[oq] = 0; }
+        return;
+    }
+
+    const uint64_t* list = p.cand + (size_t)q * p.C;
+    uint64_t pivot_hi = ~0ull, pivot_lo = ~0ull;  // ties with key <= pivot are winners
+
+    if (total_le > cap) {
+        // ---- 2b. too many survivors for shared memory: radix-select the r-th smallest key among
+        //          the ties at d*, most significant byte first (keys are unique inside a store) ----
+        uint32_t need = p.k - s_count_lt;  // >= 1
+        uint64_t pre_hi = 0, pre_lo = 0;
+        const int n_bytes = (p.key_words == 2) ? 16 : 8;
+        for (int b = 0; b < n_bytes; b++) {
+            for (uint32_t i = tid; i < 256; i += kSelectThreads) s_hist[i] = 0;
+            __syncthreads();
+            for (uint32_t i = tid; i < n_list; i += kSelectThreads) {
+                uint64_t c = list[i];
+                if (cand_rank(c) != dstar) continue;
+                const SegDesc& sd = p.segs[cand_seg(c)];
+                uint64_t hi = sd.khi[cand_row(c)];
+                uint64_t lo = (p.key_words == 2) ? sd.klo[cand_row(c)] : 0ull;
+                // top b bytes must equal the prefix found so far
+                bool match;
+                uint32_t digit;
+                if (p.key_words == 2) {
+                    if (b < 8) {
+                        match = (b == 0) || ((hi >> (64 - 8 * b)) == (pre_hi >> (64 - 8 * b)));
+                        digit = (uint32_t)(hi >> (56 - 8 * b)) & 0xffu;
+                    } else {
+                        int bb = b - 8;
+                        match = (hi == pre_hi) && ((bb == 0) || ((lo >> (64 - 8 * bb)) == (pre_lo >> (64 - 8 * bb))));
+                        digit = (uint32_t)(lo >> (56 - 8 * bb)) & 0xffu;
+                    }
+                } else {
+                    match = (b == 0) || ((hi >> (64 - 8 * b)) == (pre_hi >> (64 - 8 * b)));
+                    digit = (uint32_t)(hi >> (56 - 8 * b)) & 0xffu;
+                }
+                if (match) atomicAdd(&s_hist[digit], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t cum = 0, dsel = 255;
+                for (uint32_t d = 0; d < 256; d++) {
+                    if (cum + s_hist[d] >= need) { dsel = d; break; }
+                    cum += s_hist[d];
+                }
+                s_need = need - cum;
+                s_fill = dsel;
+            }
+            __syncthreads();
+            need = s_need;
+            uint64_t dsel = s_fill;
+            if (p.key_words == 2 && b >= 8) pre_lo |= dsel << (56 - 8 * (b - 8));
+            else pre_hi |= dsel << (56 - 8 * b);
+            __syncthreads();
+        }
+        pivot_hi = pre_hi;
+        pivot_lo = (p.key_words == 2) ? pre_lo : ~0ull;
+        if (p.key_words == 1) pivot_lo = 0;
+        if (tid == 0) s_fill = 0;
+        __syncthreads();
+    }
+
+    // ---- 2. gather survivors (rank < d*, or rank == d* and key <= pivot) into shared memory ----
+    const bool use_pivot = (total_le > cap);
+    for (uint32_t i = tid; i < n_list; i += kSelectThreads) {
+        uint64_t c = list[i];
+        uint32_t rk = cand_rank(c);
+        if (rk > dstar) continue;
+        const SegDesc& sd = p.segs[cand_seg(c)];
+        uint64_t hi = sd.khi[cand_row(c)];
+        uint64_t lo = (p.key_words == 2) ? sd.klo[cand_row(c)] : 0ull;
+        if (use_pivot && rk == dstar) {
+            bool le = (hi < pivot_hi) || (hi == pivot_hi && lo <= pivot_lo);
+            if (!le) continue;
+        }
+        uint32_t slot = atomicAdd(&s_fill, 1u);
+        if (slot < cap) {
+            s_khi[slot] = hi;
+            if (p.key_words == 2) s_klo[slot] = lo;
+            s_rk[slot] = rk;
+            s_cidx[slot] = i;
+        }
+    }
+    __syncthreads();
+    const uint32_t n_surv = min(s_fill, cap);
+    uint32_t P = 1;
+    while (P < n_surv) P <<= 1;
+    for (uint32_t i = tid; i < P; i += kSelectThreads) s_perm[i] = (i < n_surv) ? i : 0xffffffffu;
+    __syncthreads();
+
+    // ---- 3. bitonic sort of the permutation by (rank, key) ----
+    for (uint32_t size = 2; size <= P; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t i = tid; i < (P >> 1); i += kSelectThreads) {
+                uint32_t lo_i = 2 * i - (i & (stride - 1));
+                uint32_t hi_i = lo_i + stride;
+                bool asc = ((lo_i & size) == 0);
+                uint32_t pa = s_perm[lo_i], pb = s_perm[hi_i];
+                bool b_lt_a;
+                if (pb == 0xffffffffu) b_lt_a = false;
+                else if (pa == 0xffffffffu) b_lt_a = true;
+                else {
+                    SortKey ka{s_rk[pa], s_khi[pa], (p.key_words == 2) ? s_klo[pa] : 0ull};
+                    SortKey kb{s_rk[pb], s_khi[pb], (p.key_words == 2) ? s_klo[pb] : 0ull};
+                    b_lt_a = key_less(kb, ka);
+                }
+                if (b_lt_a == asc) { s_perm[lo_i] = pb; s_perm[hi_i] = pa; }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- 4. write the first n_out rows ----
+    const uint32_t n_write = min(n_out, n_surv);
+    for (uint32_t j = tid; j < p.k; j += kSelectThreads) {
+        size_t o = (size_t)oq * p.k + j;
+        if (j < n_write) {
+            uint32_t e = s_perm[j];
+            uint64_t c = list[s_cidx[e]];
+            const SegDesc& sd = p.segs[cand_seg(c)];
+            p.out_khi[o] = s_khi[e];
+            p.out_klo[o] = (p.key_words == 2) ? s_klo[e] : 0ull;
+            p.out_h[o] = (uint16_t)cand_h(c);
+            p.out_n[o] = (uint16_t)(8u * min(p.qlen_bytes, sd.len_bytes));
+        } else {
+            p.out_khi[o] = ~0ull; p.out_klo[o] = ~0ull; p.out_h[o] = 0xffffu; p.out_n[o] = 1;
+        }
+    }
+    if (p.out_codes) {
+        // stored code of every winner: words strided by cap in the segment's planes
+        for (uint32_t j = tid; j < n_write * 8; j += kSelectThreads) {
+            uint32_t e = s_perm[j >> 3], w = j & 7;
+            uint64_t c = list[s_cidx[e]];
+            const SegDesc& sd = p.segs[cand_seg(c)];
+            uint32_t v = (w < sd.words) ? sd.planes[(size_t)w * sd.cap + cand_row(c)] : 0u;
+            reinterpret_cast<uint32_t*>(p.out_codes)[((size_t)oq * p.k + (j >> 3)) * 8 + w] = v;
+        }
+    }
+    if (tid == 0) p.out_cnt[oq] = n_write;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-shard merge: every record finds its global position as the number of records (over all
+// shards) that order before it - each shard list is already sorted, so that is a sum of binary
+// searches. Order: (h/n as exact rational, key). Keys are unique across shards.
+__device__ __forceinline__ bool rec_less(uint32_t h1, uint32_t n1, uint64_t hi1, uint64_t lo1, uint32_t h2, uint32_t n2,
+                                         uint64_t hi2, uint64_t lo2) {
+    uint32_t a = h1 * n2, b = h2 * n1;  // <= 65535 * 256 fits
+    if (a != b) return a < b;
+    if (hi1 != hi2) return hi1 < hi2;
+    return lo1 < lo2;
+}
+
+__global__ void k_merge(uint32_t G, uint32_t Q, uint32_t k, const uint64_t* khi, const uint64_t* klo, const uint16_t* hh,
+                        const uint16_t* nn, const uint32_t* cnt, uint64_t* o_khi, uint64_t* o_klo, uint16_t* o_h,
+                        uint16_t* o_n, uint32_t* o_cnt) {
+    const uint32_t q = blockIdx.x;
+    uint32_t total = 0;
+    for (uint32_t g = 0; g < G; g++) total += min(cnt[(size_t)g * Q + q], k);
+    const uint32_t n_out = min(total, k);
+    for (uint32_t e = threadIdx.x; e < G * k; e += blockDim.x) {
+        uint32_t g = e / k, j = e % k;
+        if (j >= min(cnt[(size_t)g * Q + q], k)) continue;
+        size_t src = ((size_t)g * Q + q) * k + j;
+        uint32_t h1 = hh[src], n1 = nn[src];
+        uint64_t hi1 = khi[src], lo1 = klo[src];
+        uint32_t pos = j;  // records of the own list before it
+        for (uint32_t g2 = 0; g2 < G; g2++) {
+            if (g2 == g) continue;
+            size_t b2 = ((size_t)g2 * Q + q) * k;
+            uint32_t lo_i = 0, hi_i = min(cnt[(size_t)g2 * Q + q], k);
+            while (lo_i < hi_i) {  // first index whose record is not less than ours
+                uint32_t mid = (lo_i + hi_i) >> 1;
+                if (rec_less(hh[b2 + mid], nn[b2 + mid], khi[b2 + mid], klo[b2 + mid], h1, n1, hi1, lo1)) lo_i = mid + 1;
+                else hi_i = mid;
+            }
+            pos += lo_i;
+        }
+        if (pos < k) {
+            size_t o = (size_t)q * k + pos;
+            o_khi[o] = hi1; o_klo[o] = lo1; o_h[o] = (uint16_t)h1; o_n[o] = (uint16_t)n1;
+        }
+    }
+    for (uint32_t j = n_out + threadIdx.x; j < k; j += blockDim.x) {
+        size_t o = (size_t)q * k + j;
+        o_khi[o] = ~0ull; o_klo[o] = ~0ull; o_h[o] = 0xffffu; o_n[o] = 1;
+    }
+    if (threadIdx.x == 0) o_cnt[q] = n_out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Store maintenance kernels.
+// dest[i] = (segment << 32) | row, or ~0 to skip row i of the staged batch.
+__global__ void k_scatter_rows(const SegDesc* segs, const uint64_t* dest, const uint8_t* codes, const uint8_t* keys,
+                               uint32_t key_bytes, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t d = dest[i];
+    if (d == ~0ull) return;
+    const SegDesc sd = segs[(uint32_t)(d >> 32)];
+    uint32_t row = (uint32_t)d;
+    const uint32_t* c = reinterpret_cast<const uint32_t*>(codes + i * kMaxBytes);
+    for (uint32_t w = 0; w < sd.words; w++) sd.planes[(size_t)w * sd.cap + row] = c[w];
+    if (key_bytes == 8) {
+        sd.khi[row] = reinterpret_cast<const uint64_t*>(keys)[i];
+    } else {
+        const uint8_t* kb = keys + i * 16;
+        uint64_t hi = 0, lo = 0;
+        for (int b = 0; b < 8; b++) { hi = (hi << 8) | kb[b]; lo = (lo << 8) | kb[8 + b]; }
+        sd.khi[row] = hi; sd.klo[row] = lo;
+    }
+}
+
+// Ordered row moves of swap-remove: move[i] = (dst seg, dst row, src seg, src row); one warp walks
+// the list in order (moves may chain), lane w copies word w.
+__global__ void k_move_rows(const SegDesc* segs, const uint4* moves, size_t n) {
+    const uint32_t lane = threadIdx.x;
+    for (size_t i = 0; i < n; i++) {
+        uint4 mv = moves[i];
+        const SegDesc d = segs[mv.x], s = segs[mv.z];
+        if (lane < d.words) d.planes[(size_t)lane * d.cap + mv.y] = s.planes[(size_t)lane * s.cap + mv.w];
+        if (lane == 8) d.khi[mv.y] = s.khi[mv.w];
+        if (lane == 9 && d.klo) d.klo[mv.y] = s.klo[mv.w];
+        __syncwarp();
+        __threadfence_block();
+    }
+}
+
+// loc[i] = (segment << 32) | row or ~0; out: 32-byte zero padded rows
+__global__ void k_gather_rows(const SegDesc* segs, const uint64_t* loc, uint8_t* out, size_t n) {
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    uint32_t w = threadIdx.x & 7;
+    if (i >= n) return;
+    uint64_t d = loc[i];
+    uint32_t v = 0;
+    if (d != ~0ull) {
+        const SegDesc sd = segs[(uint32_t)(d >> 32)];
+        if (w < sd.words) v = sd.planes[(size_t)w * sd.cap + (uint32_t)d];
+    }
+    reinterpret_cast<uint32_t*>(out)[i * 8 + w] = v;
+}
+
+}  // namespace isx

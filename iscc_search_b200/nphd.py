@@ -1,0 +1,330 @@
+"""
+HBM-resident drop-ins for the two `iscc_usearch` classes iscc-search instantiates:
+
+* `ShardedNphdIndex`  - /root/reference/iscc_search/indexes/usearch/index.py:34, 1617-1625, 1732-1740
+                        (variable-length ISCC-UNIT bodies, uint64 ISCC-ID keys, NPHD metric)
+* `ShardedIndex128`   - /root/reference/iscc_search/indexes/simprint/usearch_core.py:26, 73-83
+                        (fixed-ndim simprints, 128-bit composite keys, Hamming metric)
+
+Same method names, argument meaning and error behaviour; the HNSW/shard knobs are accepted and
+ignored (search here is exact). All arithmetic happens in libisx_b200.so on the GPU; this module
+only converts arguments and rebuilds the float distances the reference consumes:
+NPHD distance = float32(h) / float32(nbits) (index.py:2041-2043 reads `float(distance)`),
+Hamming distance = float32(h) (tests/test_usearch_search.py:122-167).
+"""
+
+from pathlib import Path
+
+import numpy as np
+
+from iscc_search_b200._lib import Store
+from iscc_search_b200.matches import BatchMatches, Matches
+
+MAX_BYTES = 32
+SNAPSHOT_NAME = "store.isx"
+
+
+def _as_u64_keys(keys):
+    # type: (object) -> tuple[np.ndarray, bool]
+    """int | iterable of ints | uint64 array -> (uint64[n], was_scalar)."""
+    if isinstance(keys, (int, np.integer)):
+        k = int(keys)
+        if k < 0 or k >= 2**64:
+            raise ValueError(f"key {k} outside uint64 range")
+        return np.array([k], dtype=np.uint64), True
+    arr = np.asarray(keys)
+    if arr.size == 0:
+        return np.zeros(0, dtype=np.uint64), False
+    if arr.dtype != np.uint64:
+        arr = np.array([int(k) for k in arr.ravel()], dtype=np.uint64)
+    return np.ascontiguousarray(arr.ravel()), False
+
+
+def _pack_vectors(vectors, n_expected=None, fixed_len=0, max_bytes=MAX_BYTES):
+    # type: (object, int|None, int, int) -> tuple[np.ndarray, np.ndarray]
+    """bytes | uint8 1-D | 2-D array | list of bytes/arrays -> (codes uint8[n,32], lens uint8[n])."""
+    if isinstance(vectors, (bytes, bytearray, memoryview)):
+        vectors = [bytes(vectors)]
+    elif isinstance(vectors, np.ndarray) and vectors.ndim == 1:
+        vectors = [vectors]
+    if isinstance(vectors, np.ndarray) and vectors.ndim == 2:
+        n, L = vectors.shape
+        if not 1 <= L <= max_bytes:
+            raise ValueError(f"vector length {L} bytes outside 1..{max_bytes}")
+        codes = np.zeros((n, MAX_BYTES), dtype=np.uint8)
+        codes[:, :L] = vectors.astype(np.uint8, copy=False)
+        lens = np.full(n, L, dtype=np.uint8)
+    else:
+        n = len(vectors)
+        codes = np.zeros((n, MAX_BYTES), dtype=np.uint8)
+        lens = np.zeros(n, dtype=np.uint8)
+        for i, v in enumerate(vectors):
+            b = v.astype(np.uint8, copy=False).tobytes() if isinstance(v, np.ndarray) else bytes(v)
+            if not 1 <= len(b) <= max_bytes:
+                raise ValueError(f"vector {i}: length {len(b)} bytes outside 1..{max_bytes}")
+            codes[i, : len(b)] = np.frombuffer(b, dtype=np.uint8)
+            lens[i] = len(b)
+    if fixed_len and np.any(lens != fixed_len):
+        raise ValueError(f"vectors must have exactly {fixed_len * 8} bits")
+    if n_expected is not None and n != n_expected:
+        raise ValueError(f"number of keys ({n_expected}) and vectors ({n}) differ")
+    return codes, lens
+
+
+class _IndexBase:
+    """Shared lifecycle / bookkeeping of both drop-in classes."""
+
+    _key_bytes = 8
+
+    def _init_store(self, path, max_bytes, fixed_len, device):
+        self.path = Path(path) if path is not None else None
+        self._store = Store(device=device, key_bytes=self._key_bytes, max_bytes=max_bytes, fixed_len=fixed_len)
+        self._dirty = 0
+        if self.path is not None:
+            self.path.mkdir(parents=True, exist_ok=True)
+            snap = self.path / SNAPSHOT_NAME
+            if snap.exists():
+                self._store.load(snap)
+
+    # usearch / iscc-usearch surface -------------------------------------------------------
+    @property
+    def size(self):
+        return self._store.size()
+
+    def __len__(self):
+        return self._store.size()
+
+    @property
+    def dirty(self):
+        """Unsaved key mutations (auto-flush trigger, index.py:469-478)."""
+        return self._dirty
+
+    @property
+    def shard_count(self):
+        """No file shards: the store is one HBM-resident unit (0 when empty)."""
+        return 1 if self._store.size() else 0
+
+    @property
+    def serialized_length(self):
+        """Bytes a snapshot of the live rows takes (keys + codes), cf. common.py:71-108."""
+        return self._store.size() * (self._key_bytes + MAX_BYTES)
+
+    @property
+    def _active_shard_path(self):
+        return self.path / SNAPSHOT_NAME if self.path is not None else None
+
+    @property
+    def memory_usage(self):
+        return self._store.device_bytes()
+
+    def save(self):
+        """Write the snapshot (atomic rename); clears the dirty counter (index.py:883-913)."""
+        if self.path is not None:
+            self._store.save(self.path / SNAPSHOT_NAME)
+        self._dirty = 0
+
+    def drain_rotations(self):
+        """No background shard rotation exists here; kept for interface parity (index.py:934-936)."""
+
+    def reset(self):
+        """Release all in-memory (HBM) rows without touching the snapshot (index.py:1699)."""
+        self._store.clear()
+        self._dirty = 0
+
+    def close(self):
+        """Save and release resources (usearch_core.py:310-313)."""
+        if self._store is None:
+            return
+        if self._dirty and self.path is not None:
+            self.save()
+        self._store.close()
+        self._store = None
+
+    def stats(self):
+        return self._store.stats()
+
+
+class ShardedNphdIndex(_IndexBase):
+    """
+    Exact NPHD index over variable-length codes with uint64 keys.
+
+    Mirrors the constructor the reference calls (index.py:1617-1625); `connectivity`,
+    `expansion_*`, `shard_size`, `background_rotation` are HNSW / file-shard knobs with no meaning
+    for an exact HBM scan and are ignored.
+    """
+
+    _key_bytes = 8
+
+    def __init__(self, max_dim=256, path=None, connectivity=16, expansion_add=128, expansion_search=64,
+                 shard_size=512 * 1024 * 1024, background_rotation=False, device=0, **_ignored):
+        if max_dim < 8 or max_dim > 256 or max_dim % 8:
+            raise ValueError("max_dim must be a multiple of 8 bits in 8..256")
+        self.max_dim = max_dim
+        self._init_store(path, max_dim // 8, 0, device)
+
+    # -- mutation
+    def add(self, keys, vectors):
+        """
+        Add vectors (mixed lengths allowed). A key that already exists is silently skipped, first
+        wins (tests/test_usearch_add.py:53-63). Returns the keys as uint64 array like usearch.
+        """
+        k, _ = _as_u64_keys(keys)
+        codes, lens = _pack_vectors(vectors, len(k), 0, self.max_dim // 8)
+        if len(k) == 0:
+            return k
+        added = self._store.add(k, codes, lens)
+        self._dirty += int(added.sum())
+        return k
+
+    def remove(self, keys):
+        """Remove keys; missing keys are ignored. Returns the number removed (tests/test_usearch_remove.py:19-141)."""
+        k, _ = _as_u64_keys(keys)
+        if len(k) == 0:
+            return 0
+        _, cnt = self._store.remove(k, len(k))
+        self._dirty += cnt
+        return cnt
+
+    # -- lookup
+    def contains(self, keys):
+        k, scalar = _as_u64_keys(keys)
+        if len(k) == 0:
+            return np.zeros(0, dtype=bool)
+        res = self._store.contains(k, len(k))
+        return bool(res[0]) if scalar else res
+
+    def __contains__(self, key):
+        return bool(self.contains(int(key)))
+
+    def get(self, keys):
+        """Stored body WITHOUT padding as uint8 array, or None (tests/test_indexes_usearch_persistence.py:704-706)."""
+        k, scalar = _as_u64_keys(keys)
+        if len(k) == 0:
+            return []
+        codes, lens = self._store.get(k, len(k))
+        out = [codes[i, : lens[i]].copy() if lens[i] else None for i in range(len(k))]
+        return out[0] if scalar else out
+
+    # -- search
+    def search(self, vectors, count=10, exact=True, **_ignored):
+        """
+        Exact top-`count` by NPHD. 1-D input -> Matches, 2-D / list input -> BatchMatches
+        (tests/test_usearch_search.py:173-215, 374-429). `count=0` raises ValueError (:678-685).
+        """
+        if count < 1:
+            raise ValueError("`count` must be >= 1")
+        single = isinstance(vectors, (bytes, bytearray, memoryview)) or (isinstance(vectors, np.ndarray) and vectors.ndim == 1)
+        queries, qlens = _pack_vectors(vectors, None, 0, self.max_dim // 8)
+        kk = max(1, min(int(count), max(self._store.size(), 1)))
+        keys, h, nb, counts, _ = self._store.search(queries, qlens, kk)
+        dist = (h.astype(np.float32) / np.maximum(nb, 1).astype(np.float32)).astype(np.float32)
+        n_rows = self._store.size()
+        if single:
+            c = int(counts[0])
+            return Matches(keys=keys[0, :c], distances=dist[0, :c], hamming=h[0, :c], nbits=nb[0, :c],
+                           visited_members=n_rows, computed_distances=n_rows)
+        return BatchMatches(keys=keys, distances=dist, counts=counts.astype(np.int64), hamming=h, nbits=nb,
+                            visited_members=n_rows * len(qlens), computed_distances=n_rows * len(qlens))
+
+
+class ShardedIndex128(_IndexBase):
+    """
+    Exact Hamming index over fixed-`ndim` binary vectors with 128-bit composite keys
+    (`iscc_id_body(8) + offset(4) + size(4)`, big-endian - lmdb_ops.py:30-49).
+    Constructor mirrors usearch_core.py:73-83; only metric="hamming", dtype="b1" exist.
+    """
+
+    _key_bytes = 16
+
+    def __init__(self, ndim=128, metric="hamming", dtype="b1", path=None, connectivity=8, expansion_add=16,
+                 expansion_search=512, shard_size=1024 * 1024 * 1024, background_rotation=False, device=0, **_ignored):
+        if str(metric).lower() not in ("hamming", "metrickind.hamming") or str(dtype).lower() not in ("b1", "scalarkind.b1"):
+            raise ValueError("ShardedIndex128 on B200 supports metric='hamming', dtype='b1' only")
+        if ndim < 8 or ndim > 256 or ndim % 8:
+            raise ValueError("ndim must be a multiple of 8 bits in 8..256")
+        self.ndim = ndim
+        self._init_store(path, ndim // 8, ndim // 8, device)
+
+    def _normalize_batch_keys(self, keys):
+        # type: (object) -> np.ndarray
+        """list of 16-byte keys (or array) -> structured-free `V16` array (one row per key), usearch_core.py:100."""
+        if isinstance(keys, np.ndarray) and keys.dtype == np.dtype("V16"):
+            return keys
+        if isinstance(keys, (bytes, bytearray)):
+            keys = [bytes(keys)]
+        if isinstance(keys, np.ndarray) and keys.dtype == np.uint8 and keys.ndim == 2 and keys.shape[1] == 16:
+            return np.ascontiguousarray(keys).view("V16").ravel()
+        out = np.zeros(len(keys), dtype="V16")
+        buf = out.view(np.uint8).reshape(len(keys), 16)
+        for i, k in enumerate(keys):
+            b = bytes(k)
+            if len(b) != 16:
+                raise ValueError(f"key {i}: expected 16 bytes, got {len(b)}")
+            buf[i] = np.frombuffer(b, dtype=np.uint8)
+        return out
+
+    def _raw_keys(self, keys):
+        arr = self._normalize_batch_keys(keys)
+        return np.ascontiguousarray(arr.view(np.uint8).reshape(-1, 16))
+
+    def add(self, keys, vectors):
+        k = self._raw_keys(keys)
+        codes, lens = _pack_vectors(vectors, len(k), self.ndim // 8, self.ndim // 8)
+        if len(k) == 0:
+            return self._normalize_batch_keys(keys)
+        added = self._store.add(k, codes, lens)
+        self._dirty += int(added.sum())
+        return self._normalize_batch_keys(keys)
+
+    def remove(self, keys):
+        k = self._raw_keys(keys)
+        if len(k) == 0:
+            return 0
+        _, cnt = self._store.remove(k, len(k))
+        self._dirty += cnt
+        return cnt
+
+    def contains(self, keys):
+        scalar = isinstance(keys, (bytes, bytearray))
+        k = self._raw_keys(keys)
+        if len(k) == 0:
+            return np.zeros(0, dtype=bool)
+        res = self._store.contains(k, len(k))
+        return bool(res[0]) if scalar else res
+
+    def __contains__(self, key):
+        return bool(self.contains(bytes(key)))
+
+    def get(self, keys):
+        scalar = isinstance(keys, (bytes, bytearray))
+        k = self._raw_keys(keys)
+        if len(k) == 0:
+            return []
+        codes, lens = self._store.get(k, len(k))
+        out = [codes[i, : lens[i]].copy() if lens[i] else None for i in range(len(k))]
+        return out[0] if scalar else out
+
+    def search(self, vectors, count=10, exact=True, threshold_bits=None, with_vectors=False, **_ignored):
+        """
+        Exact top-`count` by Hamming distance; distances are raw bit counts as float32.
+        A single 1-D query returns a bare `Matches` (usearch_core.py:167-169), a batch `BatchMatches`.
+        `threshold_bits` (extension): keep only rows with h <= threshold_bits (h == 0: equality join).
+        `with_vectors` (extension): also return the matched stored codes (replaces `.get` per match).
+        """
+        if count < 1:
+            raise ValueError("`count` must be >= 1")
+        single = isinstance(vectors, (bytes, bytearray, memoryview)) or (isinstance(vectors, np.ndarray) and vectors.ndim == 1)
+        queries, qlens = _pack_vectors(vectors, None, self.ndim // 8, self.ndim // 8)
+        kk = max(1, min(int(count), max(self._store.size(), 1)))
+        thr = None if threshold_bits is None else (int(threshold_bits), self.ndim)
+        keys, h, nb, counts, codes = self._store.search(queries, qlens, kk, thr, with_vectors)
+        dist = h.astype(np.float32)
+        nbytes = self.ndim // 8
+        vec = codes[:, :, :nbytes] if codes is not None else None
+        n_rows = self._store.size()
+        if single:
+            c = int(counts[0])
+            return Matches(keys=keys[0, :c], distances=dist[0, :c], hamming=h[0, :c], nbits=nb[0, :c],
+                           vectors=None if vec is None else vec[0, :c], visited_members=n_rows, computed_distances=n_rows)
+        return BatchMatches(keys=keys, distances=dist, counts=counts.astype(np.int64), hamming=h, nbits=nb, vectors=vec,
+                            visited_members=n_rows * len(qlens), computed_distances=n_rows * len(qlens))

@@ -1,0 +1,143 @@
+/*
+ * ORACLE - TEST INFRASTRUCTURE ONLY. Never linked or loaded by the product path.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it.
+ *
+ * C restatement of the reference's exact (brute-force) CPU search, i.e. what
+ * `usearch.index.Index.search(..., exact=True)` does for the B1/Hamming and NPHD metrics behind
+ *   /root/reference/iscc_search/indexes/usearch/index.py:2037          (ShardedNphdIndex.search)
+ *   /root/reference/iscc_search/indexes/simprint/usearch_core.py:165   (ShardedIndex128.search)
+ * The native code lives in the un-vendored `usearch-iscc==2.24.6` (uv.lock:2491-2499), so this
+ * follows the published formula (docs/explanation/similarity-search.md:24-32):
+ *     NPHD(a,b) = popcount(a[:m]^b[:m]) / (8*m),  m = min(len a, len b) bytes
+ * Algorithm restated: linear scan of zero-padded fixed-stride rows (+1 length byte per row),
+ * one bounded top-k buffer per query, threads over queries.
+ * Order: (h/n ascending as exact rational, key ascending) - the tie rule is this project's
+ * definition (PARITY UNPINNED for ties, see oracle/nphd_oracle.py header).
+ *
+ * Validated against oracle/nphd_oracle.py (numpy) in tests/test_oracle.py.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define MAXB 32
+
+typedef struct {
+    uint64_t dnum;   /* h * (L / n) with L = common multiple -> exact integer order key */
+    uint64_t khi, klo;
+    uint32_t row;
+    uint16_t h, n;
+} cand_t;
+
+static inline int cand_less(const cand_t* a, const cand_t* b) {
+    if (a->dnum != b->dnum) return a->dnum < b->dnum;
+    if (a->khi != b->khi) return a->khi < b->khi;
+    return a->klo < b->klo;
+}
+
+/* max-heap on (dnum, key): root = current worst of the best k */
+static void heap_sift_down(cand_t* hp, size_t n, size_t i) {
+    for (;;) {
+        size_t l = 2 * i + 1, r = l + 1, m = i;
+        if (l < n && cand_less(&hp[m], &hp[l])) m = l;
+        if (r < n && cand_less(&hp[m], &hp[r])) m = r;
+        if (m == i) return;
+        cand_t t = hp[i]; hp[i] = hp[m]; hp[m] = t;
+        i = m;
+    }
+}
+static void heap_sift_up(cand_t* hp, size_t i) {
+    while (i > 0) {
+        size_t p = (i - 1) / 2;
+        if (!cand_less(&hp[p], &hp[i])) return;
+        cand_t t = hp[i]; hp[i] = hp[p]; hp[p] = t;
+        i = p;
+    }
+}
+static int cand_cmp_qsort(const void* a, const void* b) {
+    const cand_t* x = (const cand_t*)a; const cand_t* y = (const cand_t*)b;
+    if (cand_less(x, y)) return -1;
+    if (cand_less(y, x)) return 1;
+    return 0;
+}
+
+/* 8*lcm(1..32): every h/(8m) scaled by this is an exact integer < 2^63 (h <= 256) */
+static const uint64_t LCM_BITS = 8ull * 144403552893600ull;
+
+static inline uint64_t load64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }
+
+/* Hamming distance over the first m bytes (1..32) of two 32-byte zero padded rows. */
+static inline uint32_t prefix_hamming(const uint8_t* a, const uint8_t* q, uint32_t m) {
+    uint32_t full = m >> 3, rem = m & 7, h = 0;
+    for (uint32_t w = 0; w < full; w++) h += (uint32_t)__builtin_popcountll(load64(a + 8 * w) ^ load64(q + 8 * w));
+    if (rem) {
+        uint64_t mask = (1ull << (8 * rem)) - 1; /* little-endian load: first bytes are the low ones */
+        h += (uint32_t)__builtin_popcountll((load64(a + 8 * full) ^ load64(q + 8 * full)) & mask);
+    }
+    return h;
+}
+
+/*
+ * codes:   n rows x 32 bytes, zero padded;  lens: n bytes (1..32)
+ * keys_hi: n (uint64 keys, or high half of big-endian 128-bit keys); keys_lo: NULL or n
+ * queries: q rows x 32 bytes; qlens: q
+ * thr_num/thr_den: keep only h/n <= thr_num/thr_den (thr_den == 0 -> no threshold)
+ * outputs (q x k, row major): row index into the store (int64, -1 padded), h, nbits; counts[q]
+ * returns 0, or -1 on bad arguments
+ */
+int oracle_nphd_topk(const uint8_t* codes, const uint8_t* lens, const uint64_t* keys_hi, const uint64_t* keys_lo,
+                     size_t n, const uint8_t* queries, const uint8_t* qlens, size_t q, uint32_t k,
+                     uint32_t thr_num, uint32_t thr_den, int64_t* out_rows, uint16_t* out_h, uint16_t* out_n,
+                     uint32_t* counts, int n_threads) {
+    if (k < 1) return -1;
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long qi = 0; qi < (long)q; qi++) {
+        cand_t* hp = (cand_t*)malloc(sizeof(cand_t) * k);
+        size_t cnt = 0;
+        const uint8_t* qv = queries + (size_t)qi * MAXB;
+        uint32_t ql = qlens[qi];
+        if (ql < 1 || ql > MAXB || !hp) { bad = 1; counts[qi] = 0; free(hp); continue; }
+        uint64_t scale[MAXB + 1];
+        for (uint32_t m = 1; m <= MAXB; m++) scale[m] = LCM_BITS / (8ull * m);
+        uint64_t worst = UINT64_MAX; /* dnum of heap root once the heap is full */
+        for (size_t i = 0; i < n; i++) {
+            uint32_t m = lens[i] < ql ? lens[i] : ql;
+            uint32_t h = prefix_hamming(codes + i * MAXB, qv, m);
+            uint64_t dnum = (uint64_t)h * scale[m];
+            if (dnum > worst) continue;                       /* cheap reject once k are held */
+            if (thr_den && (uint64_t)h * thr_den > (uint64_t)thr_num * 8ull * m) continue;
+            cand_t c; c.dnum = dnum; c.khi = keys_hi[i]; c.klo = keys_lo ? keys_lo[i] : 0; c.row = (uint32_t)i;
+            c.h = (uint16_t)h; c.n = (uint16_t)(8 * m);
+            if (cnt < k) {
+                hp[cnt] = c; heap_sift_up(hp, cnt); cnt++;
+                if (cnt == k) worst = hp[0].dnum;
+            } else if (cand_less(&c, &hp[0])) {
+                hp[0] = c; heap_sift_down(hp, cnt, 0); worst = hp[0].dnum;
+            }
+        }
+        qsort(hp, cnt, sizeof(cand_t), cand_cmp_qsort);
+        for (size_t j = 0; j < k; j++) {
+            size_t o = (size_t)qi * k + j;
+            if (j < cnt) { out_rows[o] = hp[j].row; out_h[o] = hp[j].h; out_n[o] = hp[j].n; }
+            else { out_rows[o] = -1; out_h[o] = 0; out_n[o] = 0; }
+        }
+        counts[qi] = (uint32_t)cnt;
+        free(hp);
+    }
+    return bad ? -1 : 0;
+}
+
+int oracle_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
