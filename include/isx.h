@@ -134,11 +134,14 @@ int isx_search_device(isx_store_t* s, const uint8_t* queries, int queries_on_dev
                       uint16_t* d_hamming, uint16_t* d_nbits, uint32_t* d_counts, int sync);
 
 /*
- * Merge G per-shard result sets (device, each laid out [g][q][k] as written by isx_search_device,
- * e.g. the output of an NCCL all-gather) into the global top-k per query, same order rule.
+ * Merge G per-shard result sets (device, as written by isx_search_device and delivered by an NCCL
+ * all-gather) into the global top-k per query, same order rule. Input layout:
+ *   shard_stride_bytes == 0: each field is one dense array [g][q][k] (counts: [g][q]);
+ *   shard_stride_bytes != 0: the pointers address shard 0 and shard g's arrays start g*stride bytes
+ *                            later (every rank packed its fields into one buffer of `stride` bytes).
  * Output device arrays are q x k.  Runs on the store's stream.
  */
-int isx_merge_device(isx_store_t* s, uint32_t n_shards, size_t q, uint32_t k, const uint64_t* d_keys_hi,
+int isx_merge_device(isx_store_t* s, uint32_t n_shards, size_t q, uint32_t k, size_t shard_stride_bytes, const uint64_t* d_keys_hi,
                      const uint64_t* d_keys_lo, const uint16_t* d_hamming, const uint16_t* d_nbits,
                      const uint32_t* d_counts, uint64_t* d_out_keys_hi, uint64_t* d_out_keys_lo,
                      uint16_t* d_out_hamming, uint16_t* d_out_nbits, uint32_t* d_out_counts, int sync);

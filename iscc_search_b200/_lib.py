@@ -100,7 +100,7 @@ def lib():
     L.isx_load.argtypes = [vp, cp]
     L.isx_search.argtypes = [vp, vp, vp, sz, u32, u32, u32, vp, vp, vp, vp, vp]
     L.isx_search_device.argtypes = [vp, vp, ci, vp, sz, u32, u32, u32, vp, vp, vp, vp, vp, ci]
-    L.isx_merge_device.argtypes = [vp, u32, sz, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci]
+    L.isx_merge_device.argtypes = [vp, u32, sz, u32, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci]
     L.isx_max_k.argtypes = [vp, P(u32)]
     for name in SYMBOLS:
         if name != "isx_last_error":

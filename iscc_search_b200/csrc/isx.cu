@@ -278,7 +278,7 @@ static int build_tables(isx_store* s, uint32_t mask) {
 template <int WE, int G>
 static int launch_scan_t(isx_store* s, const ScanParams& p, uint32_t grid_cap_per_sm) {
     constexpr int QW = (WE <= 4) ? 4 : 8;
-    size_t smem = (size_t)p.T * (QW * 4 + 4 + 1) + 16;
+    size_t smem = (size_t)p.q_split * (QW * 4 + 4 + 1) + 258 * 2 + 16;
     static bool attr_done = false;
     if (!attr_done || smem > 48 * 1024) {
         CU(cudaFuncSetAttribute(k_scan<WE, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem_optin));
@@ -286,8 +286,9 @@ static int launch_scan_t(isx_store* s, const ScanParams& p, uint32_t grid_cap_pe
     }
     uint32_t n_blocks = p.block_end - p.block_begin;
     uint32_t n_items = (n_blocks + p.blocks_per_item - 1) / p.blocks_per_item;
-    uint32_t grid = std::min<uint32_t>(n_items, (uint32_t)s->sm_count * grid_cap_per_sm);
-    if (grid == 0) return 0;
+    uint32_t gx = std::min<uint32_t>(n_items, (uint32_t)s->sm_count * grid_cap_per_sm);
+    if (gx == 0) return 0;
+    dim3 grid(gx, (p.T + p.q_split - 1) / p.q_split, 1);
     k_scan<WE, G><<<grid, kThreads, smem, s->stream>>>(p);
     CU(cudaGetLastError());
     s->stats.kernel_launches++;
@@ -301,6 +302,13 @@ static int launch_scan(isx_store* s, ScanParams& p, uint32_t we, uint32_t bpi_hi
     uint32_t G = groups_for(we);
     p.blocks_per_item = std::max(G, (bpi_hint / G) * G);
     const uint32_t per_sm = 4;
+    // small ranges (bootstrap rounds): split the query tile over gridDim.y so ~2 waves of CTAs exist
+    {
+        uint32_t n_items = (p.block_end - p.block_begin + p.blocks_per_item - 1) / p.blocks_per_item;
+        uint32_t want = (uint32_t)s->sm_count * per_sm * 2;
+        uint32_t splits = n_items >= want ? 1 : std::min<uint32_t>(p.T, (want + n_items - 1) / n_items);
+        p.q_split = (p.T + splits - 1) / splits;
+    }
     switch (we) {
         case 1: return launch_scan_t<1, 4>(s, p, per_sm);
         case 2: return launch_scan_t<2, 4>(s, p, per_sm);
@@ -928,7 +936,7 @@ int isx_search_device(isx_store_t* s, const uint8_t* queries, int queries_on_dev
     return 0;
 }
 
-int isx_merge_device(isx_store_t* s, uint32_t n_shards, size_t q, uint32_t k, const uint64_t* d_keys_hi,
+int isx_merge_device(isx_store_t* s, uint32_t n_shards, size_t q, uint32_t k, size_t shard_stride_bytes, const uint64_t* d_keys_hi,
                      const uint64_t* d_keys_lo, const uint16_t* d_hamming, const uint16_t* d_nbits,
                      const uint32_t* d_counts, uint64_t* d_out_keys_hi, uint64_t* d_out_keys_lo,
                      uint16_t* d_out_hamming, uint16_t* d_out_nbits, uint32_t* d_out_counts, int sync) {
@@ -938,7 +946,7 @@ int isx_merge_device(isx_store_t* s, uint32_t n_shards, size_t q, uint32_t k, co
     std::lock_guard<std::mutex> gw(s->work_mu);
     int rc = set_device(s);
     if (rc) return rc;
-    k_merge<<<(unsigned)q, 256, 0, s->stream>>>(n_shards, (uint32_t)q, k, d_keys_hi, d_keys_lo, d_hamming, d_nbits, d_counts,
+    k_merge<<<(unsigned)q, 256, 0, s->stream>>>(n_shards, (uint32_t)q, k, shard_stride_bytes, d_keys_hi, d_keys_lo, d_hamming, d_nbits, d_counts,
                                                d_out_keys_hi, d_out_keys_lo, d_out_hamming, d_out_nbits, d_out_counts);
     CU(cudaGetLastError());
     s->stats.kernel_launches++;

@@ -58,6 +58,8 @@ struct ScanParams {
     const uint16_t* rank_tab;    // [33][257]: rank of h/(8m)
     const uint16_t* hmax_tab;    // [33][R]:  max h with rank(m, h) <= r
     uint32_t update_tau;         // 0: fixed threshold (exact re-scan)
+    uint32_t q_split;            // queries per CTA along gridDim.y (small ranges are split over queries
+                                 // so the bootstrap rounds still fill the chip)
 };
 
 __device__ __forceinline__ uint64_t pack_cand(uint32_t rank, uint32_t h, uint32_t seg, uint32_t row) {
@@ -76,16 +78,34 @@ __device__ __forceinline__ uint4 ldg_stream(const uint32_t* p) {
     return r;
 }
 
-// Rare path: a row passed the running threshold of query q.
-__device__ __noinline__ void emit_candidate(const ScanParams& p, uint32_t q, uint32_t m, uint32_t h, uint32_t seg,
-                                            uint32_t row, uint32_t seg_n, unsigned char* dirty) {
-    if (row >= seg_n) return;  // padding rows of the last group
-    uint32_t rank = p.rank_tab[m * 257 + h];
-    atomicAdd(&p.hist[(size_t)q * p.R + rank], 1u);
-    uint32_t slot = atomicAdd(&p.cand_cnt[q], 1u);
-    if (slot < p.C) p.cand[(size_t)q * p.C + slot] = pack_cand(rank, h, seg, row);
-    else p.overflow[q] = 1u;
-    dirty[q] = 1;
+// Rare path, entered by the WHOLE warp when any lane has a row within the running threshold of
+// query q: per row slot one ballot, one slot-allocating atomic per warp, fire-and-forget histogram
+// updates. `s_rank` is the rank row of this launch's compared length (shared memory).
+__device__ __noinline__ void emit_group(const ScanParams& p, uint32_t q, uint32_t hmax, uint32_t d0, uint32_t d1, uint32_t d2,
+                                        uint32_t d3, uint32_t seg, uint32_t row0, uint32_t seg_n, const uint16_t* s_rank,
+                                        unsigned char* dirty) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t d[4] = {d0, d1, d2, d3};
+    bool any = false;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const bool e = (d[r] <= hmax) && (row0 + r < seg_n);  // padding rows of the last block never emit
+        const unsigned bal = __ballot_sync(0xffffffffu, e);
+        if (bal == 0) continue;
+        any = true;
+        const int leader = __ffs(bal) - 1;
+        uint32_t base = 0;
+        if ((int)lane == leader) base = atomicAdd(&p.cand_cnt[q], (uint32_t)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (e) {
+            const uint32_t rank = s_rank[d[r]];
+            atomicAdd(&p.hist[(size_t)q * p.R + rank], 1u);
+            const uint32_t slot = base + __popc(bal & ((1u << lane) - 1u));
+            if (slot < p.C) p.cand[(size_t)q * p.C + slot] = pack_cand(rank, d[r], seg, row0 + r);
+            else p.overflow[q] = 1u;
+        }
+    }
+    if (any && lane == 0) dirty[q] = 1;
 }
 
 // Tighten tau[q] to the smallest rank t with (observed) sum_{r<=t} hist[q][r] >= k. Observed counts
@@ -118,15 +138,17 @@ template <int WE, int G>
 __global__ void __launch_bounds__(kThreads) k_scan(const __grid_constant__ ScanParams p) {
     constexpr int QW = (WE <= 4) ? 4 : 8;  // query words kept per query in shared memory
     extern __shared__ uint4 smem_raw[];
-    uint32_t* qw = reinterpret_cast<uint32_t*>(smem_raw);   // [T][QW]
-    uint32_t* hm = qw + (size_t)p.T * QW;                    // [T]
-    unsigned char* dirty = reinterpret_cast<unsigned char*>(hm + p.T);  // [T]
     const uint32_t tid = threadIdx.x;
-    const uint32_t T = p.T;
+    const uint32_t q0 = blockIdx.y * p.q_split;                 // first query of this CTA's sub-tile
+    const uint32_t T = min(p.q_split, p.T - q0);
+    uint32_t* qw = reinterpret_cast<uint32_t*>(smem_raw);       // [q_split][QW]
+    uint32_t* hm = qw + (size_t)p.q_split * QW;                 // [q_split]
+    uint16_t* s_rank = reinterpret_cast<uint16_t*>(hm + p.q_split);  // [258] rank of h at this compared length
+    unsigned char* dirty = reinterpret_cast<unsigned char*>(s_rank + 258);  // [q_split]
 
     for (uint32_t i = tid; i < T * QW; i += kThreads) {
         uint32_t q = i / QW, w = i % QW;
-        qw[i] = (w < WE) ? p.queries[q * 8 + w] : 0u;
+        qw[i] = (w < WE) ? p.queries[(size_t)(q0 + q) * 8 + w] : 0u;
     }
     for (uint32_t q = tid; q < T; q += kThreads) dirty[q] = 0;
 
@@ -135,6 +157,7 @@ __global__ void __launch_bounds__(kThreads) k_scan(const __grid_constant__ ScanP
     const uint32_t m = min(p.qlen_bytes, seg_len);               // bytes compared
     const uint32_t mask_last = (m & 3u) ? ((1u << (8u * (m & 3u))) - 1u) : 0xffffffffu;
     const uint16_t* hrow = p.hmax_tab + (size_t)m * p.R;
+    for (uint32_t i = tid; i < 257; i += kThreads) s_rank[i] = p.rank_tab[m * 257 + i];
     const uint32_t n_blocks = p.block_end - p.block_begin;
     const uint32_t n_items = (n_blocks + p.blocks_per_item - 1) / p.blocks_per_item;
 
@@ -142,7 +165,7 @@ __global__ void __launch_bounds__(kThreads) k_scan(const __grid_constant__ ScanP
         const uint32_t b_lo = p.block_begin + item * p.blocks_per_item;
         const uint32_t b_hi = min(b_lo + p.blocks_per_item, p.block_end);
         __syncthreads();  // previous item's readers of hm are done
-        for (uint32_t q = tid; q < T; q += kThreads) hm[q] = hrow[__ldcg(&p.tau[q])];
+        for (uint32_t q = tid; q < T; q += kThreads) hm[q] = hrow[__ldcg(&p.tau[q0 + q])];
         __syncthreads();
 
         for (uint32_t b = b_lo; b < b_hi; b += G) {
@@ -192,13 +215,9 @@ __global__ void __launch_bounds__(kThreads) k_scan(const __grid_constant__ ScanP
                         d2 += __popc((a[g][w].z ^ qv[w]) & mk);
                         d3 += __popc((a[g][w].w ^ qv[w]) & mk);
                     }
-                    uint32_t dmin = min(min(d0, d1), min(d2, d3));
-                    if (dmin <= hmax) {
-                        if (d0 <= hmax) emit_candidate(p, q, m, d0, seg_id[g], row0[g] + 0, seg_n[g], dirty);
-                        if (d1 <= hmax) emit_candidate(p, q, m, d1, seg_id[g], row0[g] + 1, seg_n[g], dirty);
-                        if (d2 <= hmax) emit_candidate(p, q, m, d2, seg_id[g], row0[g] + 2, seg_n[g], dirty);
-                        if (d3 <= hmax) emit_candidate(p, q, m, d3, seg_id[g], row0[g] + 3, seg_n[g], dirty);
-                    }
+                    const uint32_t dmin = min(min(d0, d1), min(d2, d3));
+                    if (__any_sync(0xffffffffu, dmin <= hmax))
+                        emit_group(p, q0 + q, hmax, d0, d1, d2, d3, seg_id[g], row0[g], seg_n[g], s_rank, dirty - q0);
                 }
             }
         }
@@ -209,7 +228,8 @@ __global__ void __launch_bounds__(kThreads) k_scan(const __grid_constant__ ScanP
             const uint32_t warp = tid >> 5, lane = tid & 31;
             for (uint32_t q = warp; q < T; q += kThreads / 32) {
                 if (dirty[q]) {
-                    tighten_tau(p, q, lane);
+                    tighten_tau(p, q0 + q, lane);
+                    __syncwarp();
                     if (lane == 0) dirty[q] = 0;
                 }
             }
@@ -476,27 +496,38 @@ __device__ __forceinline__ bool rec_less(uint32_t h1, uint32_t n1, uint64_t hi1,
     return lo1 < lo2;
 }
 
-__global__ void k_merge(uint32_t G, uint32_t Q, uint32_t k, const uint64_t* khi, const uint64_t* klo, const uint16_t* hh,
-                        const uint16_t* nn, const uint32_t* cnt, uint64_t* o_khi, uint64_t* o_klo, uint16_t* o_h,
-                        uint16_t* o_n, uint32_t* o_cnt) {
+// Field arrays of shard g start `stride` BYTES after those of shard g-1 (packed per-rank buffers as
+// an all-gather delivers them); stride 0 = dense [g][q][k] arrays per field.
+template <class T>
+__device__ __forceinline__ const T* shard_ptr(const T* base, uint32_t g, size_t stride, size_t dense_elems) {
+    return stride ? reinterpret_cast<const T*>(reinterpret_cast<const char*>(base) + (size_t)g * stride) : base + (size_t)g * dense_elems;
+}
+
+__global__ void k_merge(uint32_t G, uint32_t Q, uint32_t k, size_t stride, const uint64_t* khi, const uint64_t* klo,
+                        const uint16_t* hh, const uint16_t* nn, const uint32_t* cnt, uint64_t* o_khi, uint64_t* o_klo,
+                        uint16_t* o_h, uint16_t* o_n, uint32_t* o_cnt) {
     const uint32_t q = blockIdx.x;
+    const size_t QK = (size_t)Q * k;
     uint32_t total = 0;
-    for (uint32_t g = 0; g < G; g++) total += min(cnt[(size_t)g * Q + q], k);
+    for (uint32_t g = 0; g < G; g++) total += min(shard_ptr(cnt, g, stride, Q)[q], k);
     const uint32_t n_out = min(total, k);
     for (uint32_t e = threadIdx.x; e < G * k; e += blockDim.x) {
         uint32_t g = e / k, j = e % k;
-        if (j >= min(cnt[(size_t)g * Q + q], k)) continue;
-        size_t src = ((size_t)g * Q + q) * k + j;
-        uint32_t h1 = hh[src], n1 = nn[src];
-        uint64_t hi1 = khi[src], lo1 = klo[src];
+        if (j >= min(shard_ptr(cnt, g, stride, Q)[q], k)) continue;
+        size_t src = (size_t)q * k + j;
+        uint32_t h1 = shard_ptr(hh, g, stride, QK)[src], n1 = shard_ptr(nn, g, stride, QK)[src];
+        uint64_t hi1 = shard_ptr(khi, g, stride, QK)[src], lo1 = shard_ptr(klo, g, stride, QK)[src];
         uint32_t pos = j;  // records of the own list before it
         for (uint32_t g2 = 0; g2 < G; g2++) {
             if (g2 == g) continue;
-            size_t b2 = ((size_t)g2 * Q + q) * k;
-            uint32_t lo_i = 0, hi_i = min(cnt[(size_t)g2 * Q + q], k);
+            const uint16_t* h2 = shard_ptr(hh, g2, stride, QK) + (size_t)q * k;
+            const uint16_t* n2 = shard_ptr(nn, g2, stride, QK) + (size_t)q * k;
+            const uint64_t* hi2 = shard_ptr(khi, g2, stride, QK) + (size_t)q * k;
+            const uint64_t* lo2 = shard_ptr(klo, g2, stride, QK) + (size_t)q * k;
+            uint32_t lo_i = 0, hi_i = min(shard_ptr(cnt, g2, stride, Q)[q], k);
             while (lo_i < hi_i) {  // first index whose record is not less than ours
                 uint32_t mid = (lo_i + hi_i) >> 1;
-                if (rec_less(hh[b2 + mid], nn[b2 + mid], khi[b2 + mid], klo[b2 + mid], h1, n1, hi1, lo1)) lo_i = mid + 1;
+                if (rec_less(h2[mid], n2[mid], hi2[mid], lo2[mid], h1, n1, hi1, lo1)) lo_i = mid + 1;
                 else hi_i = mid;
             }
             pos += lo_i;

@@ -1,0 +1,103 @@
+"""
+Row-sharded exact search over the GPUs of one box: one process per GPU (`torch.distributed`, NCCL over
+NVLink), every rank scans its own rows, local top-k records are all-gathered and merged on the
+device with the same total order, so the result is independent of the number of shards
+(SURVEY.md section 8e). The reference has no multi-GPU path (manager.py:43-46) - this is new design
+behind the same `search` call shape (index.py:2037).
+
+torch is plumbing here: device buffers, the current stream and the NCCL all-gather. All arithmetic
+is in libisx_b200.so.
+"""
+
+import ctypes
+
+import numpy as np
+
+from iscc_search_b200 import _lib
+
+
+def owner_of(keys, world):
+    # type: (np.ndarray, int) -> np.ndarray
+    """Rank that stores each uint64 key: a fixed bijective mix, so placement is balanced and stable."""
+    from iscc_search_b200.synth import splitmix64
+
+    return (splitmix64(np.asarray(keys, dtype=np.uint64)) % np.uint64(world)).astype(np.int64)
+
+
+def record_layout(q, k):
+    # type: (int, int) -> tuple[dict, int]
+    """Byte offsets of the packed per-rank result buffer {khi, klo, h, n, cnt} and its 16-byte aligned size."""
+    qk = q * k
+    off = {"khi": 0, "klo": qk * 8, "h": qk * 16, "n": qk * 18, "cnt": qk * 20}
+    size = qk * 20 + q * 4
+    return off, (size + 15) // 16 * 16
+
+
+class ShardedSearcher:
+    """Search front of one rank's store; `search` is a collective call (all ranks, same arguments)."""
+
+    def __init__(self, store, rank=0, world=1, group=None, device=None):
+        import torch
+
+        self.torch = torch
+        self.store = store
+        self.rank, self.world, self.group = rank, world, group
+        self.device = torch.device("cuda", store.device) if device is None else device
+        self._bufs = {}
+
+    def _buf(self, name, nbytes):
+        t = self._bufs.get(name)
+        if t is None or t.numel() < nbytes:
+            t = self.torch.empty(max(nbytes, 256), dtype=self.torch.uint8, device=self.device)
+            self._bufs[name] = t
+        return t
+
+    def search_device(self, d_queries, qlens, k, thr=None):
+        # type: (object, np.ndarray, int, tuple|None) -> tuple
+        """
+        Queries already on the device (uint8[Q,32], zero padded). Returns the merged result as a device
+        byte buffer in `record_layout(Q, k)` form plus the layout; nothing is copied to the host.
+        """
+        torch = self.torch
+        q = len(qlens)
+        off, size = record_layout(q, k)
+        local = self._buf("local", size)
+        base = local.data_ptr()
+        tn, td = (0, 0) if thr is None else thr
+        L = _lib.lib()
+        self.store.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(L.isx_search_device(self.store.handle, d_queries.data_ptr(), 1, _lib.ptr(qlens), q, k, tn, td,
+                                       base + off["khi"], base + off["klo"], base + off["h"], base + off["n"],
+                                       base + off["cnt"], 0))
+        if self.world == 1:
+            return local, off, size
+        gathered = self._buf("gathered", size * self.world)
+        self.torch.distributed.all_gather_into_tensor(gathered[: size * self.world], local[:size], group=self.group)
+        merged = self._buf("merged", size)
+        g0, m0 = gathered.data_ptr(), merged.data_ptr()
+        _lib.check(L.isx_merge_device(self.store.handle, self.world, q, k, size, g0 + off["khi"], g0 + off["klo"],
+                                      g0 + off["h"], g0 + off["n"], g0 + off["cnt"], m0 + off["khi"], m0 + off["klo"],
+                                      m0 + off["h"], m0 + off["n"], m0 + off["cnt"], 0))
+        return merged, off, size
+
+    def search(self, queries, qlens, k, thr=None, pinned_in=None, pinned_out=None):
+        # type: (np.ndarray, np.ndarray, int, tuple|None, object, object) -> tuple
+        """Host in, host out: (keys uint64[Q,k], hamming uint16[Q,k], nbits uint16[Q,k], counts uint32[Q])."""
+        torch = self.torch
+        q = len(qlens)
+        if pinned_in is None:
+            pinned_in = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.uint8))
+        d_q = self._buf("queries", q * 32)[: q * 32].view(q, 32)
+        d_q.copy_(pinned_in.view(q, 32), non_blocking=True)
+        buf, off, size = self.search_device(d_q, qlens, k, thr)
+        if pinned_out is None:
+            pinned_out = torch.empty(size, dtype=torch.uint8, pin_memory=True)
+        pinned_out[:size].copy_(buf[:size], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        raw = pinned_out[:size].numpy()
+        qk = q * k
+        keys = raw[off["khi"]: off["khi"] + qk * 8].view(np.uint64).reshape(q, k)
+        h = raw[off["h"]: off["h"] + qk * 2].view(np.uint16).reshape(q, k)
+        nb = raw[off["n"]: off["n"] + qk * 2].view(np.uint16).reshape(q, k)
+        cnt = raw[off["cnt"]: off["cnt"] + q * 4].view(np.uint32)
+        return keys, h, nb, cnt
