@@ -32,12 +32,12 @@ def _as_u64_keys(keys):
         if k < 0 or k >= 2**64:
             raise ValueError(f"key {k} outside uint64 range")
         return np.array([k], dtype=np.uint64), True
-    arr = np.asarray(keys)
-    if arr.size == 0:
-        return np.zeros(0, dtype=np.uint64), False
-    if arr.dtype != np.uint64:
-        arr = np.array([int(k) for k in arr.ravel()], dtype=np.uint64)
-    return np.ascontiguousarray(arr.ravel()), False
+    if isinstance(keys, np.ndarray) and keys.dtype == np.uint64:
+        return np.ascontiguousarray(keys.ravel()), False
+    items = [int(k) for k in (keys.ravel() if isinstance(keys, np.ndarray) else keys)]
+    if any(k < 0 or k >= 2**64 for k in items):
+        raise ValueError("key outside uint64 range")
+    return np.array(items, dtype=np.uint64), False
 
 
 def _pack_vectors(vectors, n_expected=None, fixed_len=0, max_bytes=MAX_BYTES):

@@ -1,0 +1,122 @@
+"""
+CPU tests (no GPU): the oracle restatements against the reference's literal known-answer vectors
+(tests/golden/usearch_kats.json) and against each other (C vs numpy) on seeded inputs.
+"""
+
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from iscc_search_b200 import synth
+from oracle import c_oracle, nphd_oracle
+from oracle.nphd_oracle import StoreOracle
+
+GOLD = Path(__file__).parent / "golden"
+
+
+def test_usearch_search_kats_numpy_oracle():
+    kats = json.loads((GOLD / "usearch_kats.json").read_text())
+    for case in kats["search"]:
+        st = StoreOracle()
+        st.add([k for k, _ in case["stored"]], [bytes(v) for _, v in case["stored"]])
+        got = st.search(bytes(case["query"]), case["count"])
+        # Hamming metric: distance is the raw bit count as float32 (tests/test_usearch_search.py:122-167)
+        assert [(k, float(np.float32(h))) for k, h, _n in got] == [tuple(e) for e in case["expected"]], case["source"]
+
+
+def test_usearch_search_kats_c_oracle():
+    kats = json.loads((GOLD / "usearch_kats.json").read_text())
+    for case in kats["search"]:
+        keys = np.array([k for k, _ in case["stored"]], dtype=np.uint64)
+        codes, lens = nphd_oracle.pad_codes([bytes(v) for _, v in case["stored"]])
+        q, ql = nphd_oracle.pad_codes([bytes(case["query"])])
+        rows, h, nb, cnt = c_oracle.topk(keys, None, codes, lens, q, ql, case["count"])
+        got = [(int(keys[rows[0, j]]), float(np.float32(h[0, j]))) for j in range(cnt[0])]
+        assert got == [tuple(e) for e in case["expected"]], case["source"]
+
+
+def test_score_conversions_match_reference_literals():
+    kats = json.loads((GOLD / "usearch_kats.json").read_text())
+    sp = kats["simprint_threshold"]
+    assert nphd_oracle.simprint_score(sp["flipped_bits"], sp["ndim"]) == sp["expected_score"]
+    assert nphd_oracle.unit_score(0, 64) == kats["unit_score_identity"]["expected"]
+    assert nphd_oracle.unit_score(256, 256) == 0.0  # clamp at zero (index.py:2043)
+
+
+def test_count_zero_raises_value_error():
+    # tests/test_usearch_search.py:678-685
+    st = StoreOracle()
+    st.add([1], [b"\x01\x02\x03\x04"])
+    with pytest.raises(ValueError):
+        st.search(b"\x01\x02\x03\x04", 0)
+    with pytest.raises(ValueError):
+        c_oracle.topk(np.array([1], dtype=np.uint64), None, np.zeros((1, 32), np.uint8), np.array([4], np.uint8),
+                      np.zeros((1, 32), np.uint8), np.array([4], np.uint8), 0)
+
+
+def test_store_semantics_first_wins_remove_readd():
+    st = StoreOracle()
+    assert st.add([1, 1, 2], [b"\xb2\xcc\x3c\xf0", b"\x64\x96\xc8\xfa", b"\x01\x02\x03\x04"]) == [True, False, True]
+    assert st.get(1) == b"\xb2\xcc\x3c\xf0" and len(st) == 2          # tests/test_usearch_add.py:53-63
+    assert st.remove([1, 999]) == 1 and 1 not in st                    # tests/test_usearch_remove.py:118-141
+    assert st.add([1], [b"\x64\x96\xc8\xfa"]) == [True] and st.get(1) == b"\x64\x96\xc8\xfa"  # :226-243
+    assert (2**63 - 1) not in st and 0 not in st                       # tests/test_usearch_contains.py:214-235
+    assert st.get(12345) is None                                       # tests/test_usearch_get.py:47-56
+
+
+def test_cross_length_prefix_formula():
+    # docs/explanation/similarity-search.md:24-32: compare the common prefix, divide by its bit length
+    a = bytes([0xFF] * 8 + [0x00] * 24)   # 256-bit stored
+    q = bytes([0xFF] * 7 + [0xFE])        # 64-bit query, 1 bit off inside the prefix
+    st = StoreOracle()
+    st.add([7], [a])
+    (key, h, n), = st.search(q, 1)
+    assert (key, h, n) == (7, 1, 64)
+    assert nphd_oracle.nphd_distance_f32(np.array([h]), np.array([n]))[0] == np.float32(1) / np.float32(64)
+
+
+@pytest.mark.parametrize("seed,lengths", [(1, synth.STANDARD_LENGTHS), (2, (8,)), (3, (4, 5, 12, 13, 20, 27, 32))])
+def test_c_oracle_equals_numpy_oracle(seed, lengths):
+    n, q, k = 4000, 24, 17
+    lens = synth.make_lengths(0, n, seed, lengths)
+    codes = synth.make_codes(0, n, seed, lens)
+    keys = synth.make_keys(0, n, seed)
+    queries, qlens = synth.make_queries(q, n, seed + 1, seed, lengths, lengths)
+    ref = nphd_oracle.topk(keys, None, codes, lens, queries, qlens, k)
+    rows, h, nb, cnt = c_oracle.topk(keys, None, codes, lens, queries, qlens, k)
+    for i, (r, hh, nn) in enumerate(ref):
+        assert cnt[i] == len(r)
+        assert np.array_equal(rows[i, : cnt[i]], r) and np.array_equal(h[i, : cnt[i]], hh) and np.array_equal(nb[i, : cnt[i]], nn)
+
+
+def test_oracles_threshold_and_128bit_keys():
+    n, q, k = 3000, 10, 50
+    rng = np.random.default_rng(5)
+    codes = np.zeros((n, 32), dtype=np.uint8)
+    codes[:, :8] = rng.integers(0, 256, size=(n, 8), dtype=np.uint8)
+    codes[: n // 3, :8] = codes[0, :8]  # heavy duplicates: ties broken by the 128-bit key
+    lens = np.full(n, 8, dtype=np.uint8)
+    hi = rng.integers(0, 2**63, size=n, dtype=np.uint64) // np.uint64(1 << 40)  # few distinct asset ids
+    lo = rng.permutation(n).astype(np.uint64)
+    queries = codes[rng.integers(0, n, size=q)].copy()
+    qlens = np.full(q, 8, dtype=np.uint8)
+    for thr in (None, (16, 64), (0, 64)):
+        ref = nphd_oracle.topk(hi, lo, codes, lens, queries, qlens, k, thr)
+        rows, h, nb, cnt = c_oracle.topk(hi, lo, codes, lens, queries, qlens, k, thr)
+        for i, (r, hh, nn) in enumerate(ref):
+            assert cnt[i] == len(r) and np.array_equal(rows[i, : cnt[i]], r) and np.array_equal(h[i, : cnt[i]], hh)
+            if thr is not None:
+                assert np.all(hh.astype(np.int64) * thr[1] <= thr[0] * nn.astype(np.int64))
+
+
+def test_synth_is_deterministic_and_row_addressable():
+    a = synth.make_codes(1000, 50, 9)
+    b = synth.make_codes(0, 2000, 9)[1000:1050]
+    assert np.array_equal(a, b)
+    keys = synth.make_keys(0, 100_000, 9)
+    assert len(np.unique(keys)) == len(keys)
+    lens = synth.make_lengths(0, 40_000, 9)
+    assert set(np.unique(lens)) == set(synth.STANDARD_LENGTHS)
+    assert np.all(synth.make_codes(0, 100, 9, lens[:100])[np.arange(32)[None, :] >= lens[:100, None]] == 0)
