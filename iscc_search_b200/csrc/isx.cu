@@ -140,7 +140,7 @@ struct isx_store {
 
     // scratch
     DevBuf d_stage_codes, d_stage_keys, d_stage_dest, d_moves;
-    DevBuf d_queries, d_tau, d_hist, d_cnt, d_ovf, d_cand, d_qmap, d_fb, d_fb_cand;
+    DevBuf d_queries, d_tau, d_hist, d_shist, d_cnt, d_ovf, d_cand, d_qmap, d_fb, d_fb_cand;
     DevBuf d_out_khi, d_out_klo, d_out_h, d_out_n, d_out_cnt, d_out_codes;
     PinnedBuf h_queries, h_qmap, h_flags, h_out;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -285,8 +285,8 @@ static int launch_scan_t(isx_store* s, const ScanParams& p, uint32_t grid_cap_pe
         attr_done = true;
     }
     uint32_t n_blocks = p.block_end - p.block_begin;
-    uint32_t n_items = (n_blocks + p.blocks_per_item - 1) / p.blocks_per_item;
-    uint32_t gx = std::min<uint32_t>(n_items, (uint32_t)s->sm_count * grid_cap_per_sm);
+    uint32_t n_groups = (n_blocks + G - 1) / G;
+    uint32_t gx = std::min<uint32_t>(n_groups, (uint32_t)s->sm_count * grid_cap_per_sm);
     if (gx == 0) return 0;
     dim3 grid(gx, (p.T + p.q_split - 1) / p.q_split, 1);
     k_scan<WE, G><<<grid, kThreads, smem, s->stream>>>(p);
@@ -301,10 +301,10 @@ static uint32_t groups_for(uint32_t we) { return we <= 2 ? 4 : (we <= 4 ? 2 : 1)
 static int launch_scan(isx_store* s, ScanParams& p, uint32_t we, uint32_t bpi_hint) {
     uint32_t G = groups_for(we);
     p.blocks_per_item = std::max(G, (bpi_hint / G) * G);
-    const uint32_t per_sm = 4;
+    const uint32_t per_sm = 3;  // resident CTAs per SM (register bound, __launch_bounds__(256, 3))
     // small ranges (bootstrap rounds): split the query tile over gridDim.y so ~2 waves of CTAs exist
     {
-        uint32_t n_items = (p.block_end - p.block_begin + p.blocks_per_item - 1) / p.blocks_per_item;
+        uint32_t n_items = (p.block_end - p.block_begin + G - 1) / G;
         uint32_t want = (uint32_t)s->sm_count * per_sm * 2;
         uint32_t splits = n_items >= want ? 1 : std::min<uint32_t>(p.T, (want + n_items - 1) / n_items);
         p.q_split = (p.T + splits - 1) / splits;
@@ -325,22 +325,26 @@ static int launch_scan(isx_store* s, ScanParams& p, uint32_t we, uint32_t bpi_hi
 // Scan block range [b0, b1) of the global block list for one tile of queries; the range may span
 // several buckets, each bucket portion is one launch (uniform compared length).
 static int scan_range(isx_store* s, ScanParams& p, uint32_t b0, uint32_t b1, uint32_t bpi_hint) {
+    // buckets with L >= Lq all compare m = Lq bytes: they form ONE launch; shorter buckets one launch each
     for (uint32_t L = 1; L <= kMaxBytes; L++) {
-        uint32_t lo = std::max(b0, s->bucket_block_lo[L]), hi = std::min(b1, s->bucket_block_lo[L + 1]);
-        if (lo >= hi) continue;
-        uint32_t m = std::min(p.qlen_bytes, L);
-        p.block_begin = lo;
-        p.block_end = hi;
-        int rc = launch_scan(s, p, (m + 3) / 4, bpi_hint);
-        if (rc) return rc;
-        uint64_t rows = 0;  // live rows in the range (last block of a segment may be partial)
-        for (uint32_t b = lo; b < hi; b++) {
-            const SegDesc& d = s->segs[s->h_blocks[b].x].desc;
-            rows += std::min<uint32_t>(kBlockRows, d.n - s->h_blocks[b].y);
+        const uint32_t Lhi = (L >= p.qlen_bytes) ? kMaxBytes : L;  // last bucket of this launch
+        uint32_t lo = std::max(b0, s->bucket_block_lo[L]), hi = std::min(b1, s->bucket_block_lo[Lhi + 1]);
+        if (lo < hi) {
+            uint32_t m = std::min(p.qlen_bytes, L);
+            p.block_begin = lo;
+            p.block_end = hi;
+            int rc = launch_scan(s, p, (m + 3) / 4, bpi_hint);
+            if (rc) return rc;
+            uint64_t rows = 0;  // live rows in the range (last block of a segment may be partial)
+            for (uint32_t b = lo; b < hi; b++) {
+                const SegDesc& d = s->segs[s->h_blocks[b].x].desc;
+                rows += std::min<uint32_t>(kBlockRows, d.n - s->h_blocks[b].y);
+            }
+            s->stats.pairs += rows * p.T;
+            s->stats.algo_bytes += rows * m;
+            s->stats.algo_popc += rows * p.T * ((m + 3) / 4);
         }
-        s->stats.pairs += rows * p.T;
-        s->stats.algo_bytes += rows * m;
-        s->stats.algo_popc += rows * p.T * ((m + 3) / 4);
+        if (Lhi == kMaxBytes) break;
     }
     return 0;
 }
@@ -405,6 +409,7 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
     // bootstrap plan (block units): round 0 accepts everything over r0 blocks, then ranges grow 8x
     const uint32_t r0 = std::max<uint32_t>(1, (2 * k + kBlockRows - 1) / kBlockRows);
     uint64_t C64 = (uint64_t)r0 * kBlockRows + 40ull * k + 2048;
+    C64 = std::max<uint64_t>(C64, 32768);  // slack for the delayed threshold feedback of the first wave
     C64 = (C64 + 1023) / 1024 * 1024;
     const uint32_t C = (uint32_t)std::min<uint64_t>(C64, 1u << 26);
 
@@ -415,7 +420,7 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
     tile_max = std::min<uint32_t>(tile_max, (uint32_t)Q);
 
     if (s->d_queries.ensure(Q * 32) || s->d_qmap.ensure(Q * 4) || s->d_tau.ensure((size_t)tile_max * 4) ||
-        s->d_hist.ensure((size_t)tile_max * R * 4) || s->d_cnt.ensure((size_t)tile_max * 4) ||
+        s->d_hist.ensure((size_t)tile_max * R * 4) || s->d_shist.ensure((size_t)tile_max * R * 4) || s->d_cnt.ensure((size_t)tile_max * 4) ||
         s->d_ovf.ensure((size_t)tile_max * 4) || s->d_cand.ensure((size_t)tile_max * C * 8) ||
         s->d_fb.ensure((size_t)tile_max * 8) || s->h_flags.ensure((size_t)tile_max * 16))
         return ISX_ECUDA;
@@ -483,23 +488,36 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
                 size_t total = (size_t)T * R;
                 uint32_t grid = (uint32_t)std::min<size_t>((total + 255) / 256, (size_t)s->sm_count * 8);
                 grid = std::max<uint32_t>(grid, (T + 255) / 256);
-                k_init_queries<<<grid, 256, 0, s->stream>>>(p.tau, p.hist, p.cand_cnt, p.overflow, T, R, tau_init);
+                k_init_queries<<<grid, 256, 0, s->stream>>>(p.tau, p.hist, s->d_shist.as<uint32_t>(), p.cand_cnt, p.overflow, T, R, tau_init);
                 CU(cudaGetLastError());
                 st.kernel_launches++;
             }
             if (s->profiling) CU(cudaEventRecord(s->ev[1], s->stream));
-            // bootstrap rounds, then the bulk
-            const uint32_t wave_blocks = (uint32_t)s->sm_count * 4 * 4;  // ~ one wave of the main launch
-            uint32_t done = 0, span = r0;
-            const uint32_t bpi_main = T >= 64 ? 4 : (T >= 8 ? 8 : 16);
-            while (done < n_blocks_total) {
-                uint32_t remaining = n_blocks_total - done;
-                bool last = (span * 8 >= wave_blocks * 2) || (span >= remaining);
-                uint32_t take = last ? remaining : std::min(span, remaining);
-                if ((rc = scan_range(s, p, done, done + take, last ? bpi_main : 1))) return rc;
-                done += take;
-                span *= 8;
+            // threshold bootstrap from a stratified row sample (no emission), then one launch per bucket
+            if (n_blocks_total > 0) {
+                // batches: 256 blocks (cost ~ T*256K pairs, negligible); small tiles: ~1 % of the store, because
+                // their threshold feedback is slow relative to the scan (the first items of all CTAs run at once)
+                uint32_t want = T >= 64 ? 256 : std::min<uint32_t>(1024, std::max<uint32_t>(64, n_blocks_total / 128));
+                want = std::max<uint32_t>(want, (4 * k + kBlockRows - 1) / kBlockRows);
+                SampleParams sp{};
+                uint32_t total = 0;
+                for (uint32_t L = 1; L <= kMaxBytes; L++) {
+                    uint32_t nb = s->bucket_block_lo[L + 1] - s->bucket_block_lo[L];
+                    uint32_t take = nb ? std::min<uint32_t>(nb, std::max<uint32_t>(1, (uint32_t)(((uint64_t)want * nb + n_blocks_total - 1) / n_blocks_total))) : 0;
+                    sp.bucket_first_block[L] = s->bucket_block_lo[L];
+                    sp.prefix[L] = total;
+                    total += take;
+                }
+                sp.prefix[kMaxBytes + 1] = total;
+                size_t smem = (size_t)R * 4 + 258 * 2 + 16;
+                k_sample<<<dim3(total, T, 1), kThreads, smem, s->stream>>>(p, sp, s->d_shist.as<uint32_t>());
+                CU(cudaGetLastError());
+                k_sample_tau<<<(T * 32 + 255) / 256, 256, 0, s->stream>>>(s->d_shist.as<uint32_t>(), p.tau, T, R, k);
+                CU(cudaGetLastError());
+                st.kernel_launches += 2;
             }
+            const uint32_t bpi_main = T >= 64 ? 4 : (T >= 8 ? 8 : 16);
+            if ((rc = scan_range(s, p, 0, n_blocks_total, bpi_main))) return rc;
             if (s->profiling) CU(cudaEventRecord(s->ev[2], s->stream));
 
             SelectParams sp{};
@@ -551,17 +569,27 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
                     p2.cand = s->d_fb_cand.as<uint64_t>();
                     p2.C = (uint32_t)std::min<size_t>(C2, 0xffffffffu);
                     p2.update_tau = 0;
-                    k_init_queries<<<std::max<uint32_t>(1, (R + 255) / 256), 256, 0, s->stream>>>(p2.tau, p2.hist, p2.cand_cnt, p2.overflow, 1, R, dstar);
+                    k_init_queries<<<std::max<uint32_t>(1, (R + 255) / 256), 256, 0, s->stream>>>(p2.tau, p2.hist, nullptr, p2.cand_cnt, p2.overflow, 1, R, dstar);
                     CU(cudaGetLastError());
                     st.kernel_launches++;
+                    if (s->profiling) CU(cudaEventRecord(s->ev[1], s->stream));
                     if ((rc = scan_range(s, p2, 0, n_blocks_total, 16))) return rc;
+                    if (s->profiling) CU(cudaEventRecord(s->ev[2], s->stream));
                     SelectParams sp2 = sp;
                     sp2.cand = p2.cand; sp2.C = p2.C; sp2.T = 1; sp2.qmap = sp.qmap + qi; sp2.tau_init = dstar;
                     sp2.skip_overflowed = 0;
                     k_select<<<1, kSelectThreads, sel_smem, s->stream>>>(sp2);
                     CU(cudaGetLastError());
                     st.kernel_launches++;
+                    if (s->profiling) CU(cudaEventRecord(s->ev[3], s->stream));
                     CU(cudaStreamSynchronize(s->stream));
+                    if (s->profiling) {
+                        float a = 0, b = 0;
+                        CU(cudaEventElapsedTime(&a, s->ev[1], s->ev[2]));
+                        CU(cudaEventElapsedTime(&b, s->ev[2], s->ev[3]));
+                        st.scan_ms += a;
+                        st.select_ms += b;
+                    }
                     // NOTE: the tile's own state of slot 0 was clobbered, which is fine: the tile is finished.
                 }
             }
@@ -644,7 +672,7 @@ int isx_close(isx_store_t* s) {
     cudaStreamSynchronize(s->stream);
     free_rows(s);
     DevBuf* bufs[] = {&s->d_segs, &s->d_blocks, &s->tables.d_rank, &s->tables.d_hmax, &s->d_stage_codes, &s->d_stage_keys,
-                      &s->d_stage_dest, &s->d_moves, &s->d_queries, &s->d_tau, &s->d_hist, &s->d_cnt, &s->d_ovf, &s->d_cand,
+                      &s->d_stage_dest, &s->d_moves, &s->d_queries, &s->d_tau, &s->d_hist, &s->d_shist, &s->d_cnt, &s->d_ovf, &s->d_cand,
                       &s->d_qmap, &s->d_fb, &s->d_fb_cand, &s->d_out_khi, &s->d_out_klo, &s->d_out_h, &s->d_out_n,
                       &s->d_out_cnt, &s->d_out_codes};
     for (DevBuf* b : bufs) b->release();

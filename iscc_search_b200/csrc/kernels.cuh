@@ -133,9 +133,39 @@ __device__ __forceinline__ void tighten_tau(const ScanParams& p, uint32_t q, uin
     }
 }
 
+// Hamming distance of one row (word r of each plane vector) to the query, WE words, last word masked.
+// Carry-save compression: the POPC pipe issues 16 lanes/clk/SM against 64 for LOP3 and both overlap
+// (profiles/microbench), so three XOR words are first folded by a full adder (2 LOP3) into a sum and a
+// carry word: popc(x0)+popc(x1)+popc(x2) = popc(s) + 2*popc(c). 8 words need 5 POPC instead of 8.
+template <int WE>
+__device__ __forceinline__ uint32_t pair_distance(const uint32_t (&x)[WE]) {
+    auto csa_s = [](uint32_t a, uint32_t b, uint32_t c) { return a ^ b ^ c; };
+    auto csa_c = [](uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a ^ b)); };
+    if constexpr (WE == 1) return __popc(x[0]);
+    else if constexpr (WE == 2) return __popc(x[0]) + __popc(x[1]);
+    else if constexpr (WE == 3) return __popc(csa_s(x[0], x[1], x[2])) + 2 * __popc(csa_c(x[0], x[1], x[2]));
+    else if constexpr (WE == 4) return __popc(csa_s(x[0], x[1], x[2])) + __popc(x[3]) + 2 * __popc(csa_c(x[0], x[1], x[2]));
+    else if constexpr (WE == 5)
+        return __popc(csa_s(x[0], x[1], x[2])) + __popc(x[3]) + __popc(x[4]) + 2 * __popc(csa_c(x[0], x[1], x[2]));
+    else if constexpr (WE == 6)
+        return __popc(csa_s(x[0], x[1], x[2])) + __popc(csa_s(x[3], x[4], x[5])) +
+               2 * (__popc(csa_c(x[0], x[1], x[2])) + __popc(csa_c(x[3], x[4], x[5])));
+    else if constexpr (WE == 7) {
+        uint32_t s0 = csa_s(x[0], x[1], x[2]), s1 = csa_s(x[3], x[4], x[5]);
+        return __popc(csa_s(s0, s1, x[6])) +
+               2 * (__popc(csa_c(x[0], x[1], x[2])) + __popc(csa_c(x[3], x[4], x[5])) + __popc(csa_c(s0, s1, x[6])));
+    } else {
+        uint32_t s0 = csa_s(x[0], x[1], x[2]), s1 = csa_s(x[3], x[4], x[5]);
+        return __popc(csa_s(s0, s1, x[6])) + __popc(x[7]) +
+               2 * (__popc(csa_c(x[0], x[1], x[2])) + __popc(csa_c(x[3], x[4], x[5])) + __popc(csa_c(s0, s1, x[6])));
+    }
+}
+
 // WE: words compared per pair (1..8). G: groups of 4 rows a thread keeps in flight.
+// Work split: CTA x of the launch owns a contiguous, balanced share of the launch's block range and
+// re-reads the running thresholds every `blocks_per_item` blocks.
 template <int WE, int G>
-__global__ void __launch_bounds__(kThreads) k_scan(const __grid_constant__ ScanParams p) {
+__global__ void __launch_bounds__(kThreads, 3) k_scan(const __grid_constant__ ScanParams p) {
     constexpr int QW = (WE <= 4) ? 4 : 8;  // query words kept per query in shared memory
     extern __shared__ uint4 smem_raw[];
     const uint32_t tid = threadIdx.x;
@@ -158,15 +188,27 @@ __global__ void __launch_bounds__(kThreads) k_scan(const __grid_constant__ ScanP
     const uint32_t mask_last = (m & 3u) ? ((1u << (8u * (m & 3u))) - 1u) : 0xffffffffu;
     const uint16_t* hrow = p.hmax_tab + (size_t)m * p.R;
     for (uint32_t i = tid; i < 257; i += kThreads) s_rank[i] = p.rank_tab[m * 257 + i];
-    const uint32_t n_blocks = p.block_end - p.block_begin;
-    const uint32_t n_items = (n_blocks + p.blocks_per_item - 1) / p.blocks_per_item;
 
-    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const uint32_t b_lo = p.block_begin + item * p.blocks_per_item;
-        const uint32_t b_hi = min(b_lo + p.blocks_per_item, p.block_end);
+    const uint64_t n_blocks = p.block_end - p.block_begin;
+    const uint32_t my_lo = p.block_begin + (uint32_t)(n_blocks * blockIdx.x / gridDim.x);
+    const uint32_t my_hi = p.block_begin + (uint32_t)(n_blocks * (blockIdx.x + 1) / gridDim.x);
+    // small tiles (one query per thread at most): the next item's bound is fetched while this item streams
+    const bool prefetch = (T <= kThreads);
+    uint32_t hm_next = 0;
+    if (prefetch && tid < T) hm_next = hrow[__ldcg(&p.tau[q0 + tid])];
+
+    // item size ramps G, 2G, 4G .. blocks_per_item: the first bounds a CTA works with are the loosest
+    uint32_t item_blocks = p.update_tau ? G : p.blocks_per_item;
+    for (uint32_t b_lo = my_lo; b_lo < my_hi;) {
+        const uint32_t b_hi = min(b_lo + item_blocks, my_hi);
         __syncthreads();  // previous item's readers of hm are done
-        for (uint32_t q = tid; q < T; q += kThreads) hm[q] = hrow[__ldcg(&p.tau[q0 + q])];
+        if (prefetch && item_blocks == p.blocks_per_item) {   // steady state: bound fetched during the previous item
+            if (tid < T) hm[tid] = hm_next;
+        } else {                                              // ramp-up items: always the freshest bound
+            for (uint32_t q = tid; q < T; q += kThreads) hm[q] = hrow[__ldcg(&p.tau[q0 + q])];
+        }
         __syncthreads();
+        if (prefetch && tid < T && p.update_tau) hm_next = hrow[__ldcg(&p.tau[q0 + tid])];  // lands during the item
 
         for (uint32_t b = b_lo; b < b_hi; b += G) {
             uint4 a[G][WE];
@@ -206,15 +248,17 @@ __global__ void __launch_bounds__(kThreads) k_scan(const __grid_constant__ ScanP
                 const uint32_t hmax = hm[q];
 #pragma unroll
                 for (int g = 0; g < G; g++) {
-                    uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+                    uint32_t x0[WE], x1[WE], x2[WE], x3[WE];
 #pragma unroll
                     for (int w = 0; w < WE; w++) {
                         const uint32_t mk = (w == WE - 1) ? mask_last : 0xffffffffu;
-                        d0 += __popc((a[g][w].x ^ qv[w]) & mk);
-                        d1 += __popc((a[g][w].y ^ qv[w]) & mk);
-                        d2 += __popc((a[g][w].z ^ qv[w]) & mk);
-                        d3 += __popc((a[g][w].w ^ qv[w]) & mk);
+                        x0[w] = (a[g][w].x ^ qv[w]) & mk;
+                        x1[w] = (a[g][w].y ^ qv[w]) & mk;
+                        x2[w] = (a[g][w].z ^ qv[w]) & mk;
+                        x3[w] = (a[g][w].w ^ qv[w]) & mk;
                     }
+                    const uint32_t d0 = pair_distance<WE>(x0), d1 = pair_distance<WE>(x1);
+                    const uint32_t d2 = pair_distance<WE>(x2), d3 = pair_distance<WE>(x3);
                     const uint32_t dmin = min(min(d0, d1), min(d2, d3));
                     if (__any_sync(0xffffffffu, dmin <= hmax))
                         emit_group(p, q0 + q, hmax, d0, d1, d2, d3, seg_id[g], row0[g], seg_n[g], s_rank, dirty - q0);
@@ -234,16 +278,104 @@ __global__ void __launch_bounds__(kThreads) k_scan(const __grid_constant__ ScanP
                 }
             }
         }
+        b_lo = b_hi;
+        item_blocks = min(item_blocks * 2, p.blocks_per_item);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Threshold bootstrap: exact rank histogram of a SAMPLE of rows (blocks [block_begin, block_end) of
+// one bucket) per query, no candidates emitted. The k-th smallest rank of a subset is an upper
+// bound of the k-th smallest rank of the whole store, so tau = that rank is a safe first threshold.
+// grid = (sample blocks, queries). The sample is stratified over the buckets (a slice of the first
+// blocks of every bucket, proportional to its size), so the bound fits the whole store.
+struct SampleParams {
+    uint32_t bucket_first_block[kMaxBytes + 1];  // [L] first block of bucket L in the block list
+    uint32_t prefix[kMaxBytes + 2];              // [L] sample blocks taken from buckets < L; [33] = total
+};
+
+template <int WE>
+__device__ __forceinline__ void sample_body(const ScanParams& p, const SegDesc& sd, uint32_t blk_row, uint32_t m, uint32_t q,
+                                            uint32_t* s_hist, const uint16_t* s_rank) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t mask_last = (m & 3u) ? ((1u << (8u * (m & 3u))) - 1u) : 0xffffffffu;
+    const uint32_t row0 = blk_row + tid * 4;
+    uint32_t x0[WE], x1[WE], x2[WE], x3[WE];
+#pragma unroll
+    for (int w = 0; w < WE; w++) {
+        const uint4 a = ldg_stream(sd.planes + (size_t)w * sd.cap + row0);
+        const uint32_t qv = p.queries[(size_t)q * 8 + w];
+        const uint32_t mk = (w == WE - 1) ? mask_last : 0xffffffffu;
+        x0[w] = (a.x ^ qv) & mk; x1[w] = (a.y ^ qv) & mk; x2[w] = (a.z ^ qv) & mk; x3[w] = (a.w ^ qv) & mk;
+    }
+    const uint32_t d[4] = {pair_distance<WE>(x0), pair_distance<WE>(x1), pair_distance<WE>(x2), pair_distance<WE>(x3)};
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+        if (row0 + r < sd.n) atomicAdd(&s_hist[s_rank[d[r]]], 1u);
+}
+
+__global__ void __launch_bounds__(kThreads) k_sample(const __grid_constant__ ScanParams p, const __grid_constant__ SampleParams sp,
+                                                      uint32_t* __restrict__ sample_hist) {
+    extern __shared__ uint4 smem_raw[];
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw);       // [R]
+    uint16_t* s_rank = reinterpret_cast<uint16_t*>(s_hist + p.R);   // [258]
+    const uint32_t tid = threadIdx.x, q = blockIdx.y;
+    uint32_t L = 1;
+    while (L < kMaxBytes && blockIdx.x >= sp.prefix[L + 1]) L++;    // bucket of this sample block (uniform)
+    const uint2 blk = p.blocks[sp.bucket_first_block[L] + (blockIdx.x - sp.prefix[L])];
+    const SegDesc sd = p.segs[blk.x];
+    const uint32_t m = min(p.qlen_bytes, sd.len_bytes);
+    for (uint32_t i = tid; i < p.R; i += kThreads) s_hist[i] = 0;
+    for (uint32_t i = tid; i < 257; i += kThreads) s_rank[i] = p.rank_tab[m * 257 + i];
+    __syncthreads();
+    switch ((m + 3) / 4) {
+        case 1: sample_body<1>(p, sd, blk.y, m, q, s_hist, s_rank); break;
+        case 2: sample_body<2>(p, sd, blk.y, m, q, s_hist, s_rank); break;
+        case 3: sample_body<3>(p, sd, blk.y, m, q, s_hist, s_rank); break;
+        case 4: sample_body<4>(p, sd, blk.y, m, q, s_hist, s_rank); break;
+        case 5: sample_body<5>(p, sd, blk.y, m, q, s_hist, s_rank); break;
+        case 6: sample_body<6>(p, sd, blk.y, m, q, s_hist, s_rank); break;
+        case 7: sample_body<7>(p, sd, blk.y, m, q, s_hist, s_rank); break;
+        default: sample_body<8>(p, sd, blk.y, m, q, s_hist, s_rank); break;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < p.R; i += kThreads) {
+        const uint32_t v = s_hist[i];
+        if (v) atomicAdd(&sample_hist[(size_t)q * p.R + i], v);
+    }
+}
+
+// tau[q] = min(tau[q], smallest rank whose cumulative SAMPLE count reaches k). One warp per query.
+__global__ void k_sample_tau(const uint32_t* __restrict__ sample_hist, uint32_t* tau, uint32_t T, uint32_t R, uint32_t k) {
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= T) return;
+    const uint32_t tcur = tau[q];
+    const uint32_t* hq = sample_hist + (size_t)q * R;
+    uint32_t cum = 0;
+    for (uint32_t base = 0; base <= tcur; base += 32) {
+        const uint32_t r = base + lane;
+        uint32_t incl = (r <= tcur) ? hq[r] : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += t;
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, cum + incl >= k);
+        if (hit) {
+            if (lane == 0) tau[q] = min(tcur, base + (uint32_t)(__ffs(hit) - 1));
+            return;
+        }
+        cum += __shfl_sync(0xffffffffu, incl, 31);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // per-query state reset
-__global__ void k_init_queries(uint32_t* tau, uint32_t* hist, uint32_t* cand_cnt, uint32_t* overflow, uint32_t T,
-                               uint32_t R, uint32_t tau_init) {
+__global__ void k_init_queries(uint32_t* tau, uint32_t* hist, uint32_t* sample_hist, uint32_t* cand_cnt, uint32_t* overflow,
+                               uint32_t T, uint32_t R, uint32_t tau_init) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)T * R;
-    for (size_t j = i; j < total; j += (size_t)gridDim.x * blockDim.x) hist[j] = 0;
+    for (size_t j = i; j < total; j += (size_t)gridDim.x * blockDim.x) { hist[j] = 0; if (sample_hist) sample_hist[j] = 0; }
     if (i < T) { tau[i] = tau_init; cand_cnt[i] = 0; overflow[i] = 0; }
 }
 
