@@ -71,6 +71,8 @@ typedef struct isx_stats {
     uint64_t candidates;        /* rows that passed the running threshold (all queries) */
     uint64_t fallback_queries;  /* queries answered by the exact re-scan path (candidate overflow) */
     uint64_t passes;            /* passes over the store (query tiles) */
+    uint64_t issued_popc;       /* POPC instructions (per lane) the scan actually issues after carry-save
+                                   compression: 1,2,2,3,4,4,4,5 for 1..8 words */
 } isx_stats_t;
 
 const char* isx_last_error(void);

@@ -36,6 +36,7 @@ class IsxStats(ctypes.Structure):
         ("candidates", ctypes.c_uint64),
         ("fallback_queries", ctypes.c_uint64),
         ("passes", ctypes.c_uint64),
+        ("issued_popc", ctypes.c_uint64),
     ]
 
     def as_dict(self):

@@ -1,0 +1,56 @@
+"""torchrun worker for the N>1 tests: gloo (CPU: layout + collective plumbing only) or nccl (real sharded search)."""
+import argparse
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from iscc_search_b200 import synth  # noqa: E402
+from iscc_search_b200.sharded import owner_of, record_layout  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--backend", default="gloo")
+ap.add_argument("--out", required=True)
+args = ap.parse_args()
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+
+if args.backend == "nccl":
+    from iscc_search_b200 import _lib
+    from iscc_search_b200.sharded import ShardedSearcher
+    from tests.helpers import make_store_arrays
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    n, q, k = 400_000, 128, 100
+    keys, codes, lens = make_store_arrays(n, 31)
+    queries, qlens = synth.make_queries(q, n, 32, 31)
+    sel = owner_of(keys, world) == rank
+    st = _lib.Store(device=rank, key_bytes=8, max_bytes=32)
+    st.add(np.ascontiguousarray(keys[sel]), np.ascontiguousarray(codes[sel]), np.ascontiguousarray(lens[sel]))
+    gk, gh, gn, gc = ShardedSearcher(st, rank, world, None, torch.device("cuda", rank)).search(queries, qlens, k)
+    if rank == 0:
+        np.savez(args.out, keys=gk, h=gh, nb=gn, cnt=gc, n=n, q=q, k=k)
+    dist.barrier()
+    dist.destroy_process_group()
+else:
+    # CPU: every rank packs a deterministic fake record buffer; the all-gather must deliver them in
+    # rank order with the stride `record_layout` promises (what isx_merge_device indexes by).
+    dist.init_process_group("gloo")
+    q, k = 5, 7
+    off, size = record_layout(q, k)
+    local = torch.zeros(size, dtype=torch.uint8)
+    raw = local.numpy()
+    raw[off["khi"]: off["khi"] + q * k * 8].view(np.uint64)[:] = np.arange(q * k, dtype=np.uint64) * 10 + rank
+    raw[off["h"]: off["h"] + q * k * 2].view(np.uint16)[:] = rank + 1
+    raw[off["n"]: off["n"] + q * k * 2].view(np.uint16)[:] = 64
+    raw[off["cnt"]: off["cnt"] + q * 4].view(np.uint32)[:] = k - rank
+    gathered = torch.zeros(size * world, dtype=torch.uint8)
+    dist.all_gather_into_tensor(gathered, local)
+    if rank == 0:
+        np.savez(args.out, gathered=gathered.numpy(), size=size, world=world, q=q, k=k)
+    dist.barrier()
+    dist.destroy_process_group()
