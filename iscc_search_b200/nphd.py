@@ -213,8 +213,8 @@ class ShardedNphdIndex(_IndexBase):
         """
         if count < 1:
             raise ValueError("`count` must be >= 1")
-        single = isinstance(vectors, (bytes, bytearray, memoryview)) or (isinstance(vectors, np.ndarray) and vectors.ndim == 1)
         queries, qlens = _pack_vectors(vectors, None, 0, self.max_dim // 8)
+        single = len(qlens) == 1  # usearch returns a bare Matches for exactly one query vector, 1-D or (1, n)
         kk = max(1, min(int(count), max(self._store.size(), 1)))
         keys, h, nb, counts, _ = self._store.search(queries, qlens, kk)
         dist = (h.astype(np.float32) / np.maximum(nb, 1).astype(np.float32)).astype(np.float32)
@@ -313,8 +313,8 @@ class ShardedIndex128(_IndexBase):
         """
         if count < 1:
             raise ValueError("`count` must be >= 1")
-        single = isinstance(vectors, (bytes, bytearray, memoryview)) or (isinstance(vectors, np.ndarray) and vectors.ndim == 1)
         queries, qlens = _pack_vectors(vectors, None, self.ndim // 8, self.ndim // 8)
+        single = len(qlens) == 1  # bare Matches for one query (usearch_core.py:167-169), also for a (1, n) array
         kk = max(1, min(int(count), max(self._store.size(), 1)))
         thr = None if threshold_bits is None else (int(threshold_bits), self.ndim)
         keys, h, nb, counts, codes = self._store.search(queries, qlens, kk, thr, with_vectors)

@@ -116,6 +116,7 @@ def test_index128_composite_keys_threshold_and_equality_modes(cuda):
     assert 1.0 - float(m.distances[3]) / 64 == 0.25
     m = idx.search(base, count=10, threshold_bits=16, with_vectors=True)
     assert len(m) == 3 and np.array_equal(m.vectors[0], base)
+    assert isinstance(idx.search(base.reshape(1, -1), count=1), Matches)      # (1, n) batch -> bare Matches too
     m = idx.search(np.stack([base, flip48]), count=2, threshold_bits=0)     # equality join, capped at 2
     assert m.counts.tolist() == [2, 1] and [bytes(k) for k in m[0].keys] == [keys[2], keys[0]]
     assert idx.remove([keys[2], _ck(1, 1, 1)]) == 1 and keys[2] not in idx
