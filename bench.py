@@ -36,6 +36,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+WORKLOAD = "cfg3: 100M mixed 64/128/192/256-bit codes (25% each), exact NPHD top-k, row-sharded"
 POPC_PER_CLK_PER_SM = 15.91  # measured, profiles/microbench/r01_pipes_b200.txt
 HBM_FALLBACK_GBS = 6650.0    # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
@@ -167,19 +168,31 @@ def run_reference(args):
     ms = 1e3 * float(np.mean(times))
     value = qs / (ms * 1e-3)
     sample = f"{qs} of the {args.queries} queries x all {args.rows} rows per step"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": "exact NPHD top-k queries/s at 100M codes", "value": value, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u32 popcount", "data": "synthetic",
-        "config": {"workload": "cfg3: 100M mixed 64/128/192/256-bit codes, exact NPHD top-k", "rows": args.rows,
-                   "queries_per_step": qs, "k": args.k},
+        "config": {"workload": WORKLOAD, "rows": args.rows, "queries_per_step": args.queries, "k": args.k,
+                   "sample_queries_per_step": qs},
         "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, warnings) was sent to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # libraries that print to fd 1 (e.g. "NCCL version ...") must not pollute the JSON line
     if args.impl == "reference":
         return run_reference(args)
 
@@ -315,8 +328,7 @@ def main():
         "metric": "exact NPHD top-k queries/s at 100M codes", "value": value, "unit": "queries/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u32 popcount", "data": "synthetic",
-        "config": {"workload": "cfg3: 100M mixed 64/128/192/256-bit codes (25% each), exact NPHD top-k, row-sharded",
-                   "rows": args.rows, "rows_per_gpu": n_local, "queries_per_step": Q, "k": k,
+        "config": {"workload": WORKLOAD, "rows": args.rows, "rows_per_gpu": n_local, "queries_per_step": Q, "k": k,
                    "l2_policy": "store per GPU (>= 250 MB) exceeds the 126 MB L2; no flush needed",
                    "build_s": round(t_build, 1)},
         "codes_scanned_per_s": value * args.rows,
@@ -368,7 +380,7 @@ def main():
         out["parity"] = {"checked_queries": cores, "rows": args.rows, "bit_exact": ok}
     else:
         out["cpu_baseline"] = None
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -148,6 +148,16 @@ int isx_merge_device(isx_store_t* s, uint32_t n_shards, size_t q, uint32_t k, si
                      const uint32_t* d_counts, uint64_t* d_out_keys_hi, uint64_t* d_out_keys_lo,
                      uint16_t* d_out_hamming, uint16_t* d_out_nbits, uint32_t* d_out_counts, int sync);
 
+/*
+ * Unbounded threshold match of ONE query: every row with h/nbits <= thr_num/thr_den (thr_den != 0), in no
+ * particular order. thr = 0/1 is the bidirectional prefix match of INSTANCE codes
+ * (iscc_search/indexes/usearch/index.py:1957-2022: stored code starts with the query, or is a prefix of it).
+ * At most max_out records are written; *total_out is the number of matching rows - if it exceeds max_out
+ * call again with a larger buffer.
+ */
+int isx_match_all(isx_store_t* s, const uint8_t* query, uint32_t qlen, uint32_t thr_num, uint32_t thr_den, size_t max_out,
+                  void* keys_out, uint16_t* hamming_out, uint16_t* nbits_out, uint64_t* total_out);
+
 /* largest k isx_search accepts for this store (shared-memory bound of the final selection) */
 int isx_max_k(isx_store_t* s, uint32_t* k_out);
 

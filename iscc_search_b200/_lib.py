@@ -50,7 +50,7 @@ SYMBOLS = (
     "isx_last_error", "isx_abi_version", "isx_device_count", "isx_open", "isx_close", "isx_set_stream",
     "isx_set_profiling", "isx_get_stats", "isx_add", "isx_remove", "isx_contains", "isx_get", "isx_size",
     "isx_clear", "isx_device_bytes", "isx_length_mask", "isx_save", "isx_load", "isx_search",
-    "isx_search_device", "isx_merge_device", "isx_max_k",
+    "isx_search_device", "isx_merge_device", "isx_max_k", "isx_match_all",
 )
 
 
@@ -103,6 +103,7 @@ def lib():
     L.isx_search_device.argtypes = [vp, vp, ci, vp, sz, u32, u32, u32, vp, vp, vp, vp, vp, ci]
     L.isx_merge_device.argtypes = [vp, u32, sz, u32, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci]
     L.isx_max_k.argtypes = [vp, P(u32)]
+    L.isx_match_all.argtypes = [vp, vp, u32, u32, u32, sz, vp, vp, vp, P(u64)]
     for name in SYMBOLS:
         if name != "isx_last_error":
             getattr(L, name).restype = ci
@@ -230,6 +231,23 @@ class Store:
         tn, td = (0, 0) if thr is None else thr
         check(lib().isx_search(self.handle, ptr(queries), ptr(qlens), q, k, tn, td, ptr(keys), ptr(h), ptr(nb), ptr(counts), ptr(codes)))
         return keys, h, nb, counts, codes
+
+    def match_all(self, query, thr=(0, 1), max_out=4096):
+        # type: (bytes, tuple[int,int], int) -> tuple
+        """All rows within the threshold of one query: (keys, hamming, nbits), unordered; grows the buffer until all fit."""
+        q = np.zeros(32, dtype=np.uint8)
+        qb = bytes(query)
+        q[: len(qb)] = np.frombuffer(qb, dtype=np.uint8)
+        while True:
+            keys = np.zeros(max_out, dtype=np.uint64) if self.key_bytes == 8 else np.zeros((max_out, 16), dtype=np.uint8)
+            h = np.zeros(max_out, dtype=np.uint16)
+            nb = np.zeros(max_out, dtype=np.uint16)
+            total = ctypes.c_uint64()
+            check(lib().isx_match_all(self.handle, ptr(q), len(qb), thr[0], thr[1], max_out, ptr(keys), ptr(h), ptr(nb), ctypes.byref(total)))
+            if total.value <= max_out:
+                n = int(total.value)
+                return keys[:n], h[:n], nb[:n]
+            max_out = int(total.value) + 1024
 
     def set_stream(self, cuda_stream):
         check(lib().isx_set_stream(self.handle, ctypes.c_void_p(cuda_stream) if cuda_stream else None))

@@ -442,15 +442,15 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
         }
         CU(cudaMemcpyAsync(s->d_queries.p, hq, Q * 32, cudaMemcpyHostToDevice, s->stream));
     } else {
-        // device queries: gather rows into group order with plain 32-byte copies per run of equal order
-        size_t i = 0;
-        while (i < Q) {
-            size_t j = i + 1;
-            while (j < Q && order[j] == order[j - 1] + 1) j++;
-            CU(cudaMemcpyAsync(s->d_queries.as<uint8_t>() + i * 32, queries + (size_t)order[i] * 32, (j - i) * 32,
-                               cudaMemcpyDeviceToDevice, s->stream));
-            i = j;
-        }
+        // device queries: one gather kernel into group order (also zero-pads beyond each query's length)
+        if (s->h_queries.ensure(Q) || s->d_stage_dest.ensure(Q)) return ISX_ECUDA;
+        uint8_t* hl = s->h_queries.as<uint8_t>();
+        for (size_t i = 0; i < Q; i++) hl[i] = qlens[order[i]];
+        CU(cudaMemcpyAsync(s->d_stage_dest.p, hl, Q, cudaMemcpyHostToDevice, s->stream));
+        k_gather_queries<<<(unsigned)((Q * 8 + 255) / 256), 256, 0, s->stream>>>(reinterpret_cast<const uint32_t*>(queries), s->d_qmap.as<uint32_t>(),
+                                                                               s->d_stage_dest.as<uint8_t>(), s->d_queries.as<uint32_t>(), (uint32_t)Q);
+        CU(cudaGetLastError());
+        st.kernel_launches++;
     }
 
     if (s->profiling) CU(cudaEventRecord(s->ev[0], s->stream));
@@ -981,6 +981,81 @@ int isx_merge_device(isx_store_t* s, uint32_t n_shards, size_t q, uint32_t k, si
     CU(cudaGetLastError());
     s->stats.kernel_launches++;
     if (sync) CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int isx_match_all(isx_store_t* s, const uint8_t* query, uint32_t qlen, uint32_t thr_num, uint32_t thr_den, size_t max_out,
+                  void* keys_out, uint16_t* hamming_out, uint16_t* nbits_out, uint64_t* total_out) {
+    if (!s) return fail(ISX_EINVAL, "store is NULL");
+    if (!query || !total_out || (max_out && (!keys_out || !hamming_out || !nbits_out))) return fail(ISX_EINVAL, "NULL argument");
+    if (thr_den == 0) return fail(ISX_EINVAL, "match_all needs a threshold (thr_den != 0)");
+    if (qlen < 1 || qlen > s->max_bytes || (s->fixed_len && qlen != s->fixed_len)) return fail(ISX_EINVAL, "query length %u bytes not accepted by this index", qlen);
+    if (max_out > 0xfffffff0u) return fail(ISX_ELIMIT, "max_out too large");
+    std::shared_lock<std::shared_mutex> g(s->rows_mu);
+    std::lock_guard<std::mutex> gw(s->work_mu);
+    int rc = set_device(s);
+    if (rc) return rc;
+    isx_stats_t& st = s->stats;
+    st = isx_stats_t{};
+    *total_out = 0;
+    if ((rc = upload_segs(s)) || (rc = upload_blocks(s))) return rc;
+    const uint32_t n_blocks_total = (uint32_t)s->h_blocks.size();
+    if (n_blocks_total == 0) return 0;
+    uint32_t cmask = 1u << (qlen - 1);
+    for (uint32_t b = 1; b <= kMaxBytes; b++) if (s->bucket_rows[b]) cmask |= 1u << (std::min(qlen, b) - 1);
+    if ((rc = build_tables(s, cmask))) return rc;
+    const RankTables& tb = s->tables;
+    const uint32_t R = tb.R;
+    uint32_t tau = 0;
+    while (tau + 1 < R && (uint64_t)tb.frac_h[tau + 1] * thr_den <= (uint64_t)thr_num * tb.frac_n[tau + 1]) tau++;
+    const size_t C = std::max<size_t>(max_out, 1);
+    if (s->d_queries.ensure(32) || s->d_tau.ensure(4) || s->d_hist.ensure((size_t)R * 4) || s->d_cnt.ensure(4) || s->d_ovf.ensure(4) ||
+        s->d_fb_cand.ensure(C * 8) || s->h_flags.ensure(16) || s->d_out_khi.ensure(C * 8) || s->d_out_klo.ensure(C * 8) ||
+        s->d_out_h.ensure(C * 2) || s->d_out_n.ensure(C * 2) || s->h_queries.ensure(32))
+        return ISX_ENOMEM;
+    uint8_t* hq = s->h_queries.as<uint8_t>();
+    memset(hq, 0, 32);
+    memcpy(hq, query, qlen);
+    CU(cudaMemcpyAsync(s->d_queries.p, hq, 32, cudaMemcpyHostToDevice, s->stream));
+    ScanParams p{};
+    p.segs = s->d_segs.as<SegDesc>();
+    p.blocks = s->d_blocks.as<uint2>();
+    p.queries = s->d_queries.as<uint32_t>();
+    p.T = 1;
+    p.qlen_bytes = qlen;
+    p.tau = s->d_tau.as<uint32_t>();
+    p.hist = s->d_hist.as<uint32_t>();
+    p.cand_cnt = s->d_cnt.as<uint32_t>();
+    p.cand = s->d_fb_cand.as<uint64_t>();
+    p.overflow = s->d_ovf.as<uint32_t>();
+    p.C = (uint32_t)C; p.R = R; p.k = 1;
+    p.rank_tab = tb.d_rank.as<uint16_t>();
+    p.hmax_tab = tb.d_hmax.as<uint16_t>();
+    p.update_tau = 0;  // fixed threshold: every row within it is emitted
+    k_init_queries<<<std::max<uint32_t>(1, (R + 255) / 256), 256, 0, s->stream>>>(p.tau, p.hist, nullptr, p.cand_cnt, p.overflow, 1, R, tau);
+    CU(cudaGetLastError());
+    st.kernel_launches++;
+    if ((rc = scan_range(s, p, 0, n_blocks_total, 16))) return rc;
+    uint32_t* hf = s->h_flags.as<uint32_t>();
+    CU(cudaMemcpyAsync(hf, p.cand_cnt, 4, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    const uint32_t total = hf[0];
+    *total_out = total;
+    st.candidates = total;
+    const uint32_t n = (uint32_t)std::min<size_t>(total, max_out);
+    if (n == 0) return 0;
+    k_gather_cands<<<(n + 255) / 256, 256, 0, s->stream>>>(p.segs, p.cand, n, qlen, s->d_out_khi.as<uint64_t>(), s->d_out_klo.as<uint64_t>(),
+                                                          s->d_out_h.as<uint16_t>(), s->d_out_n.as<uint16_t>());
+    CU(cudaGetLastError());
+    st.kernel_launches++;
+    std::vector<uint64_t> khi(n), klo(n);
+    CU(cudaMemcpyAsync(khi.data(), s->d_out_khi.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s->stream));
+    if (s->key_bytes == 16) CU(cudaMemcpyAsync(klo.data(), s->d_out_klo.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(hamming_out, s->d_out_h.p, (size_t)n * 2, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(nbits_out, s->d_out_n.p, (size_t)n * 2, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if (s->key_bytes == 8) memcpy(keys_out, khi.data(), (size_t)n * 8);
+    else for (uint32_t i = 0; i < n; i++) store_key(s, keys_out, i, khi[i], klo[i]);
     return 0;
 }
 

@@ -714,6 +714,31 @@ __global__ void k_move_rows(const SegDesc* segs, const uint4* moves, size_t n) {
     }
 }
 
+// queries (device, caller order) -> group order: dst[i] = src[order[i]], 32 bytes per query, bytes beyond the
+// query's length zeroed (8 threads per query, one word each)
+__global__ void k_gather_queries(const uint32_t* src, const uint32_t* order, const uint8_t* qlens_sorted, uint32_t* dst, uint32_t Q) {
+    uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, w = threadIdx.x & 7;
+    if (i >= Q) return;
+    uint32_t v = src[(size_t)order[i] * 8 + w];
+    const uint32_t L = qlens_sorted[i];
+    if (4 * w >= L) v = 0;
+    else if (4 * w + 4 > L) v &= (1u << (8 * (L - 4 * w))) - 1u;
+    dst[(size_t)i * 8 + w] = v;
+}
+
+// candidate list -> (key, h, nbits) records, list order (used by the unbounded match-all mode)
+__global__ void k_gather_cands(const SegDesc* segs, const uint64_t* cand, uint32_t n, uint32_t qlen_bytes, uint64_t* khi,
+                               uint64_t* klo, uint16_t* hh, uint16_t* nn) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t c = cand[i];
+    const SegDesc& sd = segs[cand_seg(c)];
+    khi[i] = sd.khi[cand_row(c)];
+    klo[i] = sd.klo ? sd.klo[cand_row(c)] : 0ull;
+    hh[i] = (uint16_t)cand_h(c);
+    nn[i] = (uint16_t)(8u * min(qlen_bytes, sd.len_bytes));
+}
+
 // loc[i] = (segment << 32) | row or ~0; out: 32-byte zero padded rows
 __global__ void k_gather_rows(const SegDesc* segs, const uint64_t* loc, uint8_t* out, size_t n) {
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
