@@ -161,6 +161,27 @@ __device__ __forceinline__ uint32_t pair_distance(const uint32_t (&x)[WE]) {
     }
 }
 
+__device__ __forceinline__ uint32_t comp(const uint4& v, int r) { return r == 0 ? v.x : r == 1 ? v.y : r == 2 ? v.z : v.w; }
+
+// Cheap LOWER bound of the distance: popc(x0 | x1) <= popc(x0) + popc(x1), one POPC per word pair.
+// A row whose bound already exceeds the query's current Hamming bound cannot be a candidate, so once the
+// running threshold is tight the exact distance is only evaluated for the rare warp slots where some
+// lane's bound passes. Exact by construction (the bound never over-estimates). Pays for 2, 4, 5, 6 words.
+template <int WE>
+struct LowerBound {
+    static constexpr bool kUseful = (WE == 2 || WE == 4 || WE == 5 || WE == 6);
+    // largest Hamming bound for which the filter is expected to reject almost every random row:
+    // mean - 2.75 sigma of the bound under uniformly random codes (pairs ~ Bin(32, 3/4), singles ~ Bin(32, 1/2))
+    static constexpr uint32_t kCutoff = WE == 2 ? 17u : WE == 4 ? 38u : WE == 5 ? 50u : WE == 6 ? 60u : 0u;
+    __device__ __forceinline__ static uint32_t eval(const uint32_t (&x)[WE]) {
+        if constexpr (WE == 2) return __popc(x[0] | x[1]);
+        else if constexpr (WE == 4) return __popc(x[0] | x[1]) + __popc(x[2] | x[3]);
+        else if constexpr (WE == 5) return __popc(x[0] | x[1]) + __popc(x[2] | x[3]) + __popc(x[4]);
+        else if constexpr (WE == 6) return __popc(x[0] | x[1]) + __popc(x[2] | x[3]) + __popc(x[4] | x[5]);
+        else return 0;
+    }
+};
+
 // WE: words compared per pair (1..8). G: groups of 4 rows a thread keeps in flight.
 // Work split: CTA x of the launch owns a contiguous, balanced share of the launch's block range and
 // re-reads the running thresholds every `blocks_per_item` blocks.
@@ -246,22 +267,37 @@ __global__ void __launch_bounds__(kThreads, 3) k_scan(const __grid_constant__ Sc
                     }
                 }
                 const uint32_t hmax = hm[q];
+                const bool filtered = LowerBound<WE>::kUseful && hmax <= LowerBound<WE>::kCutoff;  // uniform per query
 #pragma unroll
                 for (int g = 0; g < G; g++) {
-                    uint32_t x0[WE], x1[WE], x2[WE], x3[WE];
+                    if (filtered) {
+                        // bound straight from the planes: (a0^q0) | ((a1^q1)&mask) is two LOP3 per word pair
+                        uint32_t lb[4];
 #pragma unroll
-                    for (int w = 0; w < WE; w++) {
-                        const uint32_t mk = (w == WE - 1) ? mask_last : 0xffffffffu;
-                        x0[w] = (a[g][w].x ^ qv[w]) & mk;
-                        x1[w] = (a[g][w].y ^ qv[w]) & mk;
-                        x2[w] = (a[g][w].z ^ qv[w]) & mk;
-                        x3[w] = (a[g][w].w ^ qv[w]) & mk;
+                        for (int r = 0; r < 4; r++) {
+                            uint32_t acc = 0;
+#pragma unroll
+                            for (int w = 0; w + 1 < WE; w += 2) {
+                                const uint32_t mk = (w + 1 == WE - 1) ? mask_last : 0xffffffffu;
+                                acc += __popc((comp(a[g][w], r) ^ qv[w]) | ((comp(a[g][w + 1], r) ^ qv[w + 1]) & mk));
+                            }
+                            if (WE & 1) acc += __popc((comp(a[g][WE - 1], r) ^ qv[WE - 1]) & mask_last);
+                            lb[r] = acc;
+                        }
+                        const uint32_t lbmin = min(min(lb[0], lb[1]), min(lb[2], lb[3]));
+                        if (!__any_sync(0xffffffffu, lbmin <= hmax)) continue;  // no lane can have a candidate in this slot
                     }
-                    const uint32_t d0 = pair_distance<WE>(x0), d1 = pair_distance<WE>(x1);
-                    const uint32_t d2 = pair_distance<WE>(x2), d3 = pair_distance<WE>(x3);
-                    const uint32_t dmin = min(min(d0, d1), min(d2, d3));
+                    uint32_t d[4];
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        uint32_t x[WE];
+#pragma unroll
+                        for (int w = 0; w < WE; w++) x[w] = (comp(a[g][w], r) ^ qv[w]) & ((w == WE - 1) ? mask_last : 0xffffffffu);
+                        d[r] = pair_distance<WE>(x);
+                    }
+                    const uint32_t dmin = min(min(d[0], d[1]), min(d[2], d[3]));
                     if (__any_sync(0xffffffffu, dmin <= hmax))
-                        emit_group(p, q0 + q, hmax, d0, d1, d2, d3, seg_id[g], row0[g], seg_n[g], s_rank, dirty - q0);
+                        emit_group(p, q0 + q, hmax, d[0], d[1], d[2], d[3], seg_id[g], row0[g], seg_n[g], s_rank, dirty - q0);
                 }
             }
         }
