@@ -144,6 +144,7 @@ struct isx_store {
     DevBuf d_out_khi, d_out_klo, d_out_h, d_out_n, d_out_cnt, d_out_codes;
     PinnedBuf h_queries, h_qmap, h_flags, h_out;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> tile_events;  // 3 per tile, grown on demand (profiling only)
     isx_stats_t stats{};
     int sm_count = 148;
     int max_smem_optin = 0;
@@ -275,13 +276,13 @@ static int build_tables(isx_store* s, uint32_t mask) {
 }
 
 // ---- scan launch dispatch ----------------------------------------------------------------------
-template <int WE, int G>
+template <int WE, int G, int MINB = 3>
 static int launch_scan_t(isx_store* s, const ScanParams& p, uint32_t grid_cap_per_sm) {
     constexpr int QW = (WE <= 4) ? 4 : 8;
     size_t smem = (size_t)p.q_split * (QW * 4 + 4 + 1) + 258 * 2 + 16;
     static bool attr_done = false;
     if (!attr_done || smem > 48 * 1024) {
-        CU(cudaFuncSetAttribute(k_scan<WE, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem_optin));
+        CU(cudaFuncSetAttribute(k_scan<WE, G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem_optin));
         attr_done = true;
     }
     uint32_t n_blocks = p.block_end - p.block_begin;
@@ -289,25 +290,42 @@ static int launch_scan_t(isx_store* s, const ScanParams& p, uint32_t grid_cap_pe
     uint32_t gx = std::min<uint32_t>(n_groups, (uint32_t)s->sm_count * grid_cap_per_sm);
     if (gx == 0) return 0;
     dim3 grid(gx, (p.T + p.q_split - 1) / p.q_split, 1);
-    k_scan<WE, G><<<grid, kThreads, smem, s->stream>>>(p);
+    k_scan<WE, G, MINB><<<grid, kThreads, smem, s->stream>>>(p);
     CU(cudaGetLastError());
     s->stats.kernel_launches++;
     s->stats.scan_launches++;
     return 0;
 }
 
-static uint32_t groups_for(uint32_t we) { return we <= 2 ? 4 : (we <= 4 ? 2 : 1); }
+static int g_variant = -1;  // experiment switch (env ISX_VARIANT): 0 = default, 1 = 4 CTAs/SM with smaller row groups
+static uint32_t groups_for(uint32_t we) {
+    if (g_variant == 1) return we <= 2 ? 2 : 1;
+    return we <= 2 ? 4 : (we <= 4 ? 2 : 1);
+}
 
 static int launch_scan(isx_store* s, ScanParams& p, uint32_t we, uint32_t bpi_hint) {
+    if (g_variant < 0) { const char* e = getenv("ISX_VARIANT"); g_variant = e ? atoi(e) : 0; }
     uint32_t G = groups_for(we);
     p.blocks_per_item = std::max(G, (bpi_hint / G) * G);
-    const uint32_t per_sm = 3;  // resident CTAs per SM (register bound, __launch_bounds__(256, 3))
+    const uint32_t per_sm = g_variant == 1 ? 4 : 3;  // resident CTAs per SM (register bound)
     // small ranges (bootstrap rounds): split the query tile over gridDim.y so ~2 waves of CTAs exist
     {
         uint32_t n_items = (p.block_end - p.block_begin + G - 1) / G;
         uint32_t want = (uint32_t)s->sm_count * per_sm * 2;
         uint32_t splits = n_items >= want ? 1 : std::min<uint32_t>(p.T, (want + n_items - 1) / n_items);
         p.q_split = (p.T + splits - 1) / splits;
+    }
+    if (g_variant == 1) {
+        switch (we) {
+            case 1: return launch_scan_t<1, 2, 4>(s, p, per_sm);
+            case 2: return launch_scan_t<2, 2, 4>(s, p, per_sm);
+            case 3: return launch_scan_t<3, 1, 4>(s, p, per_sm);
+            case 4: return launch_scan_t<4, 1, 4>(s, p, per_sm);
+            case 5: return launch_scan_t<5, 1, 4>(s, p, per_sm);
+            case 6: return launch_scan_t<6, 1, 4>(s, p, per_sm);
+            case 7: return launch_scan_t<7, 1, 4>(s, p, per_sm);
+            case 8: return launch_scan_t<8, 1, 4>(s, p, per_sm);
+        }
     }
     switch (we) {
         case 1: return launch_scan_t<1, 4>(s, p, per_sm);
@@ -462,84 +480,151 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
         CU(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem_optin - (int)fa.sharedSizeBytes));
     }
 
-    size_t g0 = 0;
-    while (g0 < Q) {
+    // ---- all tiles are enqueued without host synchronisation; overflow flags, candidate counts and the
+    //      (d*, count<=d*) pairs of every tile land in pinned memory and are inspected once at the end ----
+    struct Tile { size_t t0; uint32_t T, Lq; };
+    std::vector<Tile> tiles;
+    for (size_t g0 = 0; g0 < Q;) {
         const uint32_t Lq = qlens[order[g0]];
         size_t g1 = g0;
         while (g1 < Q && qlens[order[g1]] == Lq) g1++;
-        for (size_t t0 = g0; t0 < g1; t0 += tile_max) {
-            const uint32_t T = (uint32_t)std::min<size_t>(tile_max, g1 - t0);
-            st.passes++;
-            ScanParams p{};
-            p.segs = s->d_segs.as<SegDesc>();
-            p.blocks = s->d_blocks.as<uint2>();
-            p.queries = s->d_queries.as<uint32_t>() + t0 * 8;
-            p.T = T;
-            p.qlen_bytes = Lq;
-            p.tau = s->d_tau.as<uint32_t>();
-            p.hist = s->d_hist.as<uint32_t>();
-            p.cand_cnt = s->d_cnt.as<uint32_t>();
-            p.cand = s->d_cand.as<uint64_t>();
-            p.overflow = s->d_ovf.as<uint32_t>();
-            p.C = C; p.R = R; p.k = k;
-            p.rank_tab = tb.d_rank.as<uint16_t>();
-            p.hmax_tab = tb.d_hmax.as<uint16_t>();
-            p.update_tau = 1;
+        for (size_t t0 = g0; t0 < g1; t0 += tile_max) tiles.push_back(Tile{t0, (uint32_t)std::min<size_t>(tile_max, g1 - t0), Lq});
+        g0 = g1;
+    }
+    if (s->h_flags.ensure(Q * 16)) return ISX_ENOMEM;
+    uint32_t* hf_ovf = s->h_flags.as<uint32_t>();  // [Q] overflow flags | [Q] candidate counts | [Q][2] (d*, count_le)
+    uint32_t* hf_cnt = hf_ovf + Q;
+    uint32_t* hf_info = hf_cnt + Q;
+    if (s->profiling)
+        while (s->tile_events.size() < tiles.size() * 3) {
+            cudaEvent_t e;
+            CU(cudaEventCreate(&e));
+            s->tile_events.push_back(e);
+        }
 
-            {
-                size_t total = (size_t)T * R;
-                uint32_t grid = (uint32_t)std::min<size_t>((total + 255) / 256, (size_t)s->sm_count * 8);
-                grid = std::max<uint32_t>(grid, (T + 255) / 256);
-                k_init_queries<<<grid, 256, 0, s->stream>>>(p.tau, p.hist, s->d_shist.as<uint32_t>(), p.cand_cnt, p.overflow, T, R, tau_init);
-                CU(cudaGetLastError());
-                st.kernel_launches++;
+    auto make_params = [&](const Tile& t) {
+        ScanParams p{};
+        p.segs = s->d_segs.as<SegDesc>();
+        p.blocks = s->d_blocks.as<uint2>();
+        p.queries = s->d_queries.as<uint32_t>() + t.t0 * 8;
+        p.T = t.T;
+        p.qlen_bytes = t.Lq;
+        p.tau = s->d_tau.as<uint32_t>();
+        p.hist = s->d_hist.as<uint32_t>();
+        p.cand_cnt = s->d_cnt.as<uint32_t>();
+        p.cand = s->d_cand.as<uint64_t>();
+        p.overflow = s->d_ovf.as<uint32_t>();
+        p.C = C; p.R = R; p.k = k;
+        p.rank_tab = tb.d_rank.as<uint16_t>();
+        p.hmax_tab = tb.d_hmax.as<uint16_t>();
+        p.update_tau = 1;
+        return p;
+    };
+    auto make_select = [&](const Tile& t, const ScanParams& p) {
+        SelectParams sp{};
+        sp.segs = p.segs; sp.hist = p.hist; sp.cand_cnt = p.cand_cnt; sp.cand = p.cand; sp.overflow = p.overflow;
+        sp.qmap = s->d_qmap.as<uint32_t>() + t.t0;
+        sp.C = C; sp.R = R; sp.k = k; sp.T = t.T; sp.qlen_bytes = t.Lq; sp.sort_cap = sort_cap; sp.key_words = key_words;
+        sp.tau_init = tau_init;
+        sp.out_khi = out.khi; sp.out_klo = out.klo; sp.out_h = out.h; sp.out_n = out.n; sp.out_cnt = out.cnt;
+        sp.out_codes = out.codes;
+        sp.fallback_info = s->d_fb.as<uint32_t>();
+        sp.skip_overflowed = 1;
+        return sp;
+    };
+
+    for (size_t ti = 0; ti < tiles.size(); ti++) {
+        const Tile& t = tiles[ti];
+        const uint32_t T = t.T, Lq = t.Lq;
+        st.passes++;
+        ScanParams p = make_params(t);
+        {
+            size_t total = (size_t)T * R;
+            uint32_t grid = (uint32_t)std::min<size_t>((total + 255) / 256, (size_t)s->sm_count * 8);
+            grid = std::max<uint32_t>(grid, (T + 255) / 256);
+            k_init_queries<<<grid, 256, 0, s->stream>>>(p.tau, p.hist, s->d_shist.as<uint32_t>(), p.cand_cnt, p.overflow, T, R, tau_init);
+            CU(cudaGetLastError());
+            st.kernel_launches++;
+        }
+        if (s->profiling) CU(cudaEventRecord(s->tile_events[3 * ti], s->stream));
+        // threshold bootstrap from a stratified row sample (no emission), then one launch per compared length
+        if (n_blocks_total > 0) {
+            // batches: 256 blocks (cost ~ T*256K pairs, negligible); small tiles: ~1 % of the store, because
+            // their threshold feedback is slow relative to the scan (the first items of all CTAs run at once)
+            uint32_t want = T >= 64 ? 256 : std::min<uint32_t>(1024, std::max<uint32_t>(64, n_blocks_total / 128));
+            want = std::max<uint32_t>(want, (4 * k + kBlockRows - 1) / kBlockRows);
+            SampleParams sp{};
+            uint32_t total = 0;
+            for (uint32_t L = 1; L <= kMaxBytes; L++) {
+                uint32_t nb = s->bucket_block_lo[L + 1] - s->bucket_block_lo[L];
+                uint32_t take = nb ? std::min<uint32_t>(nb, std::max<uint32_t>(1, (uint32_t)(((uint64_t)want * nb + n_blocks_total - 1) / n_blocks_total))) : 0;
+                sp.bucket_first_block[L] = s->bucket_block_lo[L];
+                sp.prefix[L] = total;
+                total += take;
             }
+            sp.prefix[kMaxBytes + 1] = total;
+            size_t smem = (size_t)R * 4 + 258 * 2 + 16;
+            k_sample<<<dim3(total, T, 1), kThreads, smem, s->stream>>>(p, sp, s->d_shist.as<uint32_t>());
+            CU(cudaGetLastError());
+            k_sample_tau<<<(T * 32 + 255) / 256, 256, 0, s->stream>>>(s->d_shist.as<uint32_t>(), p.tau, T, R, k);
+            CU(cudaGetLastError());
+            st.kernel_launches += 2;
+        }
+        const uint32_t bpi_main = T >= 64 ? 4 : (T >= 8 ? 8 : 16);
+        if ((rc = scan_range(s, p, 0, n_blocks_total, bpi_main))) return rc;
+        if (s->profiling) CU(cudaEventRecord(s->tile_events[3 * ti + 1], s->stream));
+
+        SelectParams sp = make_select(t, p);
+        k_select<<<T, kSelectThreads, sel_smem, s->stream>>>(sp);
+        CU(cudaGetLastError());
+        st.kernel_launches++;
+        if (s->profiling) CU(cudaEventRecord(s->tile_events[3 * ti + 2], s->stream));
+        // per-tile flags to pinned memory, no synchronisation (the state buffers are reused by the next tile in stream order)
+        CU(cudaMemcpyAsync(hf_ovf + t.t0, p.overflow, (size_t)T * 4, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(hf_cnt + t.t0, p.cand_cnt, (size_t)T * 4, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(hf_info + 2 * t.t0, sp.fallback_info, (size_t)T * 8, cudaMemcpyDeviceToHost, s->stream));
+        (void)Lq;
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    if (s->profiling) {
+        for (size_t ti = 0; ti < tiles.size(); ti++) {
+            float a = 0, b = 0;
+            CU(cudaEventElapsedTime(&a, s->tile_events[3 * ti], s->tile_events[3 * ti + 1]));
+            CU(cudaEventElapsedTime(&b, s->tile_events[3 * ti + 1], s->tile_events[3 * ti + 2]));
+            st.scan_ms += a;
+            st.select_ms += b;
+        }
+    }
+    for (size_t i = 0; i < Q; i++) st.candidates += hf_cnt[i];
+
+    // exact re-scan of overflowed queries, one at a time: their histogram was still exact, so d* and the
+    // number of rows with rank <= d* are known; collect exactly those rows with the fixed threshold d*.
+    for (const Tile& t : tiles) {
+        for (uint32_t qi = 0; qi < t.T; qi++) {
+            if (!hf_ovf[t.t0 + qi]) continue;
+            st.fallback_queries++;
+            const uint32_t dstar = hf_info[2 * (t.t0 + qi)], count_le = hf_info[2 * (t.t0 + qi) + 1];
+            const size_t C2 = (size_t)count_le + 1024;
+            if (s->d_fb_cand.ensure(C2 * 8)) return ISX_ENOMEM;
+            ScanParams p2 = make_params(t);
+            p2.queries += (size_t)qi * 8;
+            p2.T = 1;
+            p2.cand = s->d_fb_cand.as<uint64_t>();
+            p2.C = (uint32_t)std::min<size_t>(C2, 0xffffffffu);
+            p2.update_tau = 0;
+            k_init_queries<<<std::max<uint32_t>(1, (R + 255) / 256), 256, 0, s->stream>>>(p2.tau, p2.hist, nullptr, p2.cand_cnt, p2.overflow, 1, R, dstar);
+            CU(cudaGetLastError());
+            st.kernel_launches++;
             if (s->profiling) CU(cudaEventRecord(s->ev[1], s->stream));
-            // threshold bootstrap from a stratified row sample (no emission), then one launch per bucket
-            if (n_blocks_total > 0) {
-                // batches: 256 blocks (cost ~ T*256K pairs, negligible); small tiles: ~1 % of the store, because
-                // their threshold feedback is slow relative to the scan (the first items of all CTAs run at once)
-                uint32_t want = T >= 64 ? 256 : std::min<uint32_t>(1024, std::max<uint32_t>(64, n_blocks_total / 128));
-                want = std::max<uint32_t>(want, (4 * k + kBlockRows - 1) / kBlockRows);
-                SampleParams sp{};
-                uint32_t total = 0;
-                for (uint32_t L = 1; L <= kMaxBytes; L++) {
-                    uint32_t nb = s->bucket_block_lo[L + 1] - s->bucket_block_lo[L];
-                    uint32_t take = nb ? std::min<uint32_t>(nb, std::max<uint32_t>(1, (uint32_t)(((uint64_t)want * nb + n_blocks_total - 1) / n_blocks_total))) : 0;
-                    sp.bucket_first_block[L] = s->bucket_block_lo[L];
-                    sp.prefix[L] = total;
-                    total += take;
-                }
-                sp.prefix[kMaxBytes + 1] = total;
-                size_t smem = (size_t)R * 4 + 258 * 2 + 16;
-                k_sample<<<dim3(total, T, 1), kThreads, smem, s->stream>>>(p, sp, s->d_shist.as<uint32_t>());
-                CU(cudaGetLastError());
-                k_sample_tau<<<(T * 32 + 255) / 256, 256, 0, s->stream>>>(s->d_shist.as<uint32_t>(), p.tau, T, R, k);
-                CU(cudaGetLastError());
-                st.kernel_launches += 2;
-            }
-            const uint32_t bpi_main = T >= 64 ? 4 : (T >= 8 ? 8 : 16);
-            if ((rc = scan_range(s, p, 0, n_blocks_total, bpi_main))) return rc;
+            if ((rc = scan_range(s, p2, 0, n_blocks_total, 16))) return rc;
             if (s->profiling) CU(cudaEventRecord(s->ev[2], s->stream));
-
-            SelectParams sp{};
-            sp.segs = p.segs; sp.hist = p.hist; sp.cand_cnt = p.cand_cnt; sp.cand = p.cand; sp.overflow = p.overflow;
-            sp.qmap = s->d_qmap.as<uint32_t>() + t0;
-            sp.C = C; sp.R = R; sp.k = k; sp.T = T; sp.qlen_bytes = Lq; sp.sort_cap = sort_cap; sp.key_words = key_words;
-            sp.tau_init = tau_init;
-            sp.out_khi = out.khi; sp.out_klo = out.klo; sp.out_h = out.h; sp.out_n = out.n; sp.out_cnt = out.cnt;
-            sp.out_codes = out.codes;
-            sp.fallback_info = s->d_fb.as<uint32_t>();
-            sp.skip_overflowed = 1;
-            k_select<<<T, kSelectThreads, sel_smem, s->stream>>>(sp);
+            SelectParams sp2 = make_select(t, p2);
+            sp2.cand = p2.cand; sp2.C = p2.C; sp2.T = 1; sp2.qmap += qi; sp2.tau_init = dstar;
+            sp2.skip_overflowed = 0;
+            k_select<<<1, kSelectThreads, sel_smem, s->stream>>>(sp2);
             CU(cudaGetLastError());
             st.kernel_launches++;
             if (s->profiling) CU(cudaEventRecord(s->ev[3], s->stream));
-
-            // overflow flags + candidate counts back to the host (tiny)
-            uint32_t* hf = s->h_flags.as<uint32_t>();
-            CU(cudaMemcpyAsync(hf, p.overflow, (size_t)T * 4, cudaMemcpyDeviceToHost, s->stream));
-            CU(cudaMemcpyAsync(hf + T, p.cand_cnt, (size_t)T * 4, cudaMemcpyDeviceToHost, s->stream));
             CU(cudaStreamSynchronize(s->stream));
             if (s->profiling) {
                 float a = 0, b = 0;
@@ -548,57 +633,10 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
                 st.scan_ms += a;
                 st.select_ms += b;
             }
-            std::vector<uint32_t> fb;
-            for (uint32_t i = 0; i < T; i++) {
-                st.candidates += hf[T + i];
-                if (hf[i]) fb.push_back(i);
-            }
-            if (!fb.empty()) {
-                // exact re-scan of the overflowed queries, one at a time: the histogram is still exact,
-                // so d* and the number of rows with rank <= d* are known; collect exactly those rows.
-                CU(cudaMemcpyAsync(hf + 2 * T, s->d_fb.p, (size_t)T * 8, cudaMemcpyDeviceToHost, s->stream));
-                CU(cudaStreamSynchronize(s->stream));
-                std::vector<uint32_t> info(hf + 2 * T, hf + 2 * T + 2 * T);
-                for (uint32_t qi : fb) {
-                    st.fallback_queries++;
-                    uint32_t dstar = info[2 * qi], count_le = info[2 * qi + 1];
-                    size_t C2 = (size_t)count_le + 1024;
-                    if (s->d_fb_cand.ensure(C2 * 8)) return ISX_ENOMEM;
-                    ScanParams p2 = p;
-                    p2.queries = p.queries + (size_t)qi * 8;
-                    p2.T = 1;
-                    // state block of query 0 of the tile is free to reuse now (its results are written)
-                    p2.cand = s->d_fb_cand.as<uint64_t>();
-                    p2.C = (uint32_t)std::min<size_t>(C2, 0xffffffffu);
-                    p2.update_tau = 0;
-                    k_init_queries<<<std::max<uint32_t>(1, (R + 255) / 256), 256, 0, s->stream>>>(p2.tau, p2.hist, nullptr, p2.cand_cnt, p2.overflow, 1, R, dstar);
-                    CU(cudaGetLastError());
-                    st.kernel_launches++;
-                    if (s->profiling) CU(cudaEventRecord(s->ev[1], s->stream));
-                    if ((rc = scan_range(s, p2, 0, n_blocks_total, 16))) return rc;
-                    if (s->profiling) CU(cudaEventRecord(s->ev[2], s->stream));
-                    SelectParams sp2 = sp;
-                    sp2.cand = p2.cand; sp2.C = p2.C; sp2.T = 1; sp2.qmap = sp.qmap + qi; sp2.tau_init = dstar;
-                    sp2.skip_overflowed = 0;
-                    k_select<<<1, kSelectThreads, sel_smem, s->stream>>>(sp2);
-                    CU(cudaGetLastError());
-                    st.kernel_launches++;
-                    if (s->profiling) CU(cudaEventRecord(s->ev[3], s->stream));
-                    CU(cudaStreamSynchronize(s->stream));
-                    if (s->profiling) {
-                        float a = 0, b = 0;
-                        CU(cudaEventElapsedTime(&a, s->ev[1], s->ev[2]));
-                        CU(cudaEventElapsedTime(&b, s->ev[2], s->ev[3]));
-                        st.scan_ms += a;
-                        st.select_ms += b;
-                    }
-                    // NOTE: the tile's own state of slot 0 was clobbered, which is fine: the tile is finished.
-                }
-            }
         }
-        g0 = g1;
     }
     if (s->profiling) {
+        CU(cudaEventRecord(s->ev[3], s->stream));
         CU(cudaStreamSynchronize(s->stream));
         float t = 0;
         CU(cudaEventElapsedTime(&t, s->ev[0], s->ev[3]));
@@ -681,6 +719,7 @@ int isx_close(isx_store_t* s) {
     PinnedBuf* pbufs[] = {&s->h_queries, &s->h_qmap, &s->h_flags, &s->h_out};
     for (PinnedBuf* b : pbufs) b->release();
     for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : s->tile_events) cudaEventDestroy(ev);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
     return 0;

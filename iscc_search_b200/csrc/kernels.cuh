@@ -185,8 +185,8 @@ struct LowerBound {
 // WE: words compared per pair (1..8). G: groups of 4 rows a thread keeps in flight.
 // Work split: CTA x of the launch owns a contiguous, balanced share of the launch's block range and
 // re-reads the running thresholds every `blocks_per_item` blocks.
-template <int WE, int G>
-__global__ void __launch_bounds__(kThreads, 3) k_scan(const __grid_constant__ ScanParams p) {
+template <int WE, int G, int MINB = 3>
+__global__ void __launch_bounds__(kThreads, MINB) k_scan(const __grid_constant__ ScanParams p) {
     constexpr int QW = (WE <= 4) ? 4 : 8;  // query words kept per query in shared memory
     extern __shared__ uint4 smem_raw[];
     const uint32_t tid = threadIdx.x;
