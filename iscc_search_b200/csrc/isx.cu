@@ -116,6 +116,8 @@ struct isx_store {
     int device = 0;
     uint32_t key_bytes = 8, max_bytes = 32, fixed_len = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};  // the launches of one pass run concurrently (tails overlap)
+    cudaEvent_t fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
     bool profiling = false;
 
     std::shared_mutex rows_mu;  // shared: search/get/contains; exclusive: add/remove/clear/load
@@ -277,7 +279,7 @@ static int build_tables(isx_store* s, uint32_t mask) {
 
 // ---- scan launch dispatch ----------------------------------------------------------------------
 template <int WE, int G, int MINB = 3>
-static int launch_scan_t(isx_store* s, const ScanParams& p, uint32_t grid_cap_per_sm) {
+static int launch_scan_t(isx_store* s, const ScanParams& p, uint32_t grid_cap_per_sm, cudaStream_t stream) {
     constexpr int QW = (WE <= 4) ? 4 : 8;
     size_t smem = (size_t)p.q_split * (QW * 4 + 4 + 1) + 258 * 2 + 16;
     static bool attr_done = false;
@@ -290,7 +292,7 @@ static int launch_scan_t(isx_store* s, const ScanParams& p, uint32_t grid_cap_pe
     uint32_t gx = std::min<uint32_t>(n_groups, (uint32_t)s->sm_count * grid_cap_per_sm);
     if (gx == 0) return 0;
     dim3 grid(gx, (p.T + p.q_split - 1) / p.q_split, 1);
-    k_scan<WE, G, MINB><<<grid, kThreads, smem, s->stream>>>(p);
+    k_scan<WE, G, MINB><<<grid, kThreads, smem, stream>>>(p);
     CU(cudaGetLastError());
     s->stats.kernel_launches++;
     s->stats.scan_launches++;
@@ -303,7 +305,7 @@ static uint32_t groups_for(uint32_t we) {
     return we <= 2 ? 4 : (we <= 4 ? 2 : 1);
 }
 
-static int launch_scan(isx_store* s, ScanParams& p, uint32_t we, uint32_t bpi_hint) {
+static int launch_scan(isx_store* s, ScanParams& p, uint32_t we, uint32_t bpi_hint, cudaStream_t stream) {
     if (g_variant < 0) { const char* e = getenv("ISX_VARIANT"); g_variant = e ? atoi(e) : 0; }
     uint32_t G = groups_for(we);
     p.blocks_per_item = std::max(G, (bpi_hint / G) * G);
@@ -317,25 +319,25 @@ static int launch_scan(isx_store* s, ScanParams& p, uint32_t we, uint32_t bpi_hi
     }
     if (g_variant == 1) {
         switch (we) {
-            case 1: return launch_scan_t<1, 2, 4>(s, p, per_sm);
-            case 2: return launch_scan_t<2, 2, 4>(s, p, per_sm);
-            case 3: return launch_scan_t<3, 1, 4>(s, p, per_sm);
-            case 4: return launch_scan_t<4, 1, 4>(s, p, per_sm);
-            case 5: return launch_scan_t<5, 1, 4>(s, p, per_sm);
-            case 6: return launch_scan_t<6, 1, 4>(s, p, per_sm);
-            case 7: return launch_scan_t<7, 1, 4>(s, p, per_sm);
-            case 8: return launch_scan_t<8, 1, 4>(s, p, per_sm);
+            case 1: return launch_scan_t<1, 2, 4>(s, p, per_sm, stream);
+            case 2: return launch_scan_t<2, 2, 4>(s, p, per_sm, stream);
+            case 3: return launch_scan_t<3, 1, 4>(s, p, per_sm, stream);
+            case 4: return launch_scan_t<4, 1, 4>(s, p, per_sm, stream);
+            case 5: return launch_scan_t<5, 1, 4>(s, p, per_sm, stream);
+            case 6: return launch_scan_t<6, 1, 4>(s, p, per_sm, stream);
+            case 7: return launch_scan_t<7, 1, 4>(s, p, per_sm, stream);
+            case 8: return launch_scan_t<8, 1, 4>(s, p, per_sm, stream);
         }
     }
     switch (we) {
-        case 1: return launch_scan_t<1, 4>(s, p, per_sm);
-        case 2: return launch_scan_t<2, 4>(s, p, per_sm);
-        case 3: return launch_scan_t<3, 2>(s, p, per_sm);
-        case 4: return launch_scan_t<4, 2>(s, p, per_sm);
-        case 5: return launch_scan_t<5, 1>(s, p, per_sm);
-        case 6: return launch_scan_t<6, 1>(s, p, per_sm);
-        case 7: return launch_scan_t<7, 1>(s, p, per_sm);
-        case 8: return launch_scan_t<8, 1>(s, p, per_sm);
+        case 1: return launch_scan_t<1, 4>(s, p, per_sm, stream);
+        case 2: return launch_scan_t<2, 4>(s, p, per_sm, stream);
+        case 3: return launch_scan_t<3, 2>(s, p, per_sm, stream);
+        case 4: return launch_scan_t<4, 2>(s, p, per_sm, stream);
+        case 5: return launch_scan_t<5, 1>(s, p, per_sm, stream);
+        case 6: return launch_scan_t<6, 1>(s, p, per_sm, stream);
+        case 7: return launch_scan_t<7, 1>(s, p, per_sm, stream);
+        case 8: return launch_scan_t<8, 1>(s, p, per_sm, stream);
     }
     return fail(ISX_EINVAL, "bad word count %u", we);
 }
@@ -343,7 +345,10 @@ static int launch_scan(isx_store* s, ScanParams& p, uint32_t we, uint32_t bpi_hi
 // Scan block range [b0, b1) of the global block list for one tile of queries; the range may span
 // several buckets, each bucket portion is one launch (uniform compared length).
 static int scan_range(isx_store* s, ScanParams& p, uint32_t b0, uint32_t b1, uint32_t bpi_hint) {
-    // buckets with L >= Lq all compare m = Lq bytes: they form ONE launch; shorter buckets one launch each
+    // buckets with L >= Lq all compare m = Lq bytes: they form ONE launch; shorter buckets one launch each.
+    // The launches of a pass are independent (they only share the monotone thresholds), so the 2nd..4th go to
+    // side streams forked from / joined back into the store's stream: their ramp-up and tails overlap.
+    int n_launch = 0, side_used = 0;
     for (uint32_t L = 1; L <= kMaxBytes; L++) {
         const uint32_t Lhi = (L >= p.qlen_bytes) ? kMaxBytes : L;  // last bucket of this launch
         uint32_t lo = std::max(b0, s->bucket_block_lo[L]), hi = std::min(b1, s->bucket_block_lo[Lhi + 1]);
@@ -351,8 +356,19 @@ static int scan_range(isx_store* s, ScanParams& p, uint32_t b0, uint32_t b1, uin
             uint32_t m = std::min(p.qlen_bytes, L);
             p.block_begin = lo;
             p.block_end = hi;
-            int rc = launch_scan(s, p, (m + 3) / 4, bpi_hint);
+            cudaStream_t stream = s->stream;
+            if (n_launch > 0 && side_used < 3) {
+                if (side_used == 0) CU(cudaEventRecord(s->fork_ev, s->stream));
+                stream = s->side[side_used];
+                CU(cudaStreamWaitEvent(stream, s->fork_ev, 0));
+            }
+            int rc = launch_scan(s, p, (m + 3) / 4, bpi_hint, stream);
             if (rc) return rc;
+            if (stream != s->stream) {
+                CU(cudaEventRecord(s->join_ev[side_used], stream));
+                side_used++;
+            }
+            n_launch++;
             uint64_t rows = 0;  // live rows in the range (last block of a segment may be partial)
             for (uint32_t b = lo; b < hi; b++) {
                 const SegDesc& d = s->segs[s->h_blocks[b].x].desc;
@@ -366,6 +382,7 @@ static int scan_range(isx_store* s, ScanParams& p, uint32_t b0, uint32_t b1, uin
         }
         if (Lhi == kMaxBytes) break;
     }
+    for (int i = 0; i < side_used; i++) CU(cudaStreamWaitEvent(s->stream, s->join_ev[i], 0));
     return 0;
 }
 
@@ -691,6 +708,11 @@ int isx_open(isx_store_t** out, int device, uint32_t key_bytes, uint32_t max_byt
     s->stream = s->own_stream;
     for (auto& ev : s->ev)
         if (cudaEventCreate(&ev) != cudaSuccess) { delete s; return fail(ISX_ECUDA, "cudaEventCreate failed"); }
+    for (int i = 0; i < 3; i++) {
+        if (cudaStreamCreateWithFlags(&s->side[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s->join_ev[i], cudaEventDisableTiming) != cudaSuccess) { delete s; return fail(ISX_ECUDA, "side stream setup failed"); }
+    }
+    if (cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming) != cudaSuccess) { delete s; return fail(ISX_ECUDA, "cudaEventCreate failed"); }
     *out = s;
     return 0;
 }
@@ -720,6 +742,8 @@ int isx_close(isx_store_t* s) {
     for (PinnedBuf* b : pbufs) b->release();
     for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : s->tile_events) cudaEventDestroy(ev);
+    for (int i = 0; i < 3; i++) { if (s->side[i]) cudaStreamDestroy(s->side[i]); if (s->join_ev[i]) cudaEventDestroy(s->join_ev[i]); }
+    if (s->fork_ev) cudaEventDestroy(s->fork_ev);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
     return 0;
