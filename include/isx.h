@@ -71,8 +71,9 @@ typedef struct isx_stats {
     uint64_t candidates;        /* rows that passed the running threshold (all queries) */
     uint64_t fallback_queries;  /* queries answered by the exact re-scan path (candidate overflow) */
     uint64_t passes;            /* passes over the store (query tiles) */
-    uint64_t issued_popc;       /* POPC instructions (per lane) the scan actually issues after carry-save
-                                   compression: 1,2,2,3,4,4,4,5 for 1..8 words */
+    uint64_t issued_popc;       /* POPC (per lane) the scan issues in steady state: lower-bound filter for 2,4,5,6
+                                   words, carry-save otherwise: 1,1,2,2,3,3,4,5 for 1..8 words (estimate: while a
+                                   query's threshold is still loose the exact path adds its carry-save count) */
 } isx_stats_t;
 
 const char* isx_last_error(void);
