@@ -299,35 +299,19 @@ static int launch_scan_t(isx_store* s, const ScanParams& p, uint32_t grid_cap_pe
     return 0;
 }
 
-static int g_variant = -1;  // experiment switch (env ISX_VARIANT): 0 = default, 1 = 4 CTAs/SM with smaller row groups
-static uint32_t groups_for(uint32_t we) {
-    if (g_variant == 1) return we <= 2 ? 2 : 1;
-    return we <= 2 ? 4 : (we <= 4 ? 2 : 1);
-}
+static uint32_t groups_for(uint32_t we) { return we <= 2 ? 4 : (we <= 4 ? 2 : 1); }
 
 static int launch_scan(isx_store* s, ScanParams& p, uint32_t we, uint32_t bpi_hint, cudaStream_t stream) {
-    if (g_variant < 0) { const char* e = getenv("ISX_VARIANT"); g_variant = e ? atoi(e) : 0; }
     uint32_t G = groups_for(we);
     p.blocks_per_item = std::max(G, (bpi_hint / G) * G);
-    const uint32_t per_sm = g_variant == 1 ? 4 : 3;  // resident CTAs per SM (register bound)
-    // small ranges (bootstrap rounds): split the query tile over gridDim.y so ~2 waves of CTAs exist
+    const uint32_t per_sm = 3;  // resident CTAs per SM (register bound, __launch_bounds__(256, 3); 4 CTAs of 64
+                                // registers measured no faster - the POPC pipe, not occupancy, is the limit)
+    // small ranges: split the query tile over gridDim.y so ~2 waves of CTAs exist
     {
         uint32_t n_items = (p.block_end - p.block_begin + G - 1) / G;
         uint32_t want = (uint32_t)s->sm_count * per_sm * 2;
         uint32_t splits = n_items >= want ? 1 : std::min<uint32_t>(p.T, (want + n_items - 1) / n_items);
         p.q_split = (p.T + splits - 1) / splits;
-    }
-    if (g_variant == 1) {
-        switch (we) {
-            case 1: return launch_scan_t<1, 2, 4>(s, p, per_sm, stream);
-            case 2: return launch_scan_t<2, 2, 4>(s, p, per_sm, stream);
-            case 3: return launch_scan_t<3, 1, 4>(s, p, per_sm, stream);
-            case 4: return launch_scan_t<4, 1, 4>(s, p, per_sm, stream);
-            case 5: return launch_scan_t<5, 1, 4>(s, p, per_sm, stream);
-            case 6: return launch_scan_t<6, 1, 4>(s, p, per_sm, stream);
-            case 7: return launch_scan_t<7, 1, 4>(s, p, per_sm, stream);
-            case 8: return launch_scan_t<8, 1, 4>(s, p, per_sm, stream);
-        }
     }
     switch (we) {
         case 1: return launch_scan_t<1, 4>(s, p, per_sm, stream);

@@ -37,6 +37,20 @@ def test_search_raw_matches_reference_fixtures(cuda):
         idx.close()
 
 
+def test_search_raw_with_index_doc_frequencies_equals_callback_path(cuda):
+    # doc_freq_fn="index": one batched equality join instead of one lookup per simprint - same numbers
+    for case in GOLD["search_raw"][:9]:
+        idx = _build(case["rows"], case["ndim"])
+        idx.oversampling_factor = case["oversampling"]
+        doc_freq = case["doc_freq"]
+        query = [bytes.fromhex(q) for q in case["query"]]
+        assert idx.doc_freqs(query) == {q: doc_freq.get(q.hex(), 0) for q in query}
+        got = idx.search_raw(query, limit=case["limit"], threshold=case["threshold"], detailed=True, doc_freq_fn="index",
+                             total_assets=case["total_assets"])
+        _check_results(got, case["result"])
+        idx.close()
+
+
 def test_search_exact_and_doc_freq_match_reference_fixtures(cuda):
     for case in GOLD["search_exact"]:
         idx = _build(case["rows"], 64)
