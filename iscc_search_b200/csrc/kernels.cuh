@@ -195,7 +195,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_scan(const __grid_constant__
     uint32_t* qw = reinterpret_cast<uint32_t*>(smem_raw);       // [q_split][QW]
     uint32_t* hm = qw + (size_t)p.q_split * QW;                 // [q_split]
     uint16_t* s_rank = reinterpret_cast<uint16_t*>(hm + p.q_split);  // [258] rank of h at this compared length
-    unsigned char* dirty = reinterpret_cast<unsigned char*>(s_rank + 258);  // [q_split]
+    uint16_t* s_hrow = s_rank + 258;                                 // [R rounded up to even] largest h within rank r
+    unsigned char* dirty = reinterpret_cast<unsigned char*>(s_hrow + ((p.R + 1) & ~1u));  // [q_split]
 
     for (uint32_t i = tid; i < T * QW; i += kThreads) {
         uint32_t q = i / QW, w = i % QW;
@@ -207,8 +208,10 @@ __global__ void __launch_bounds__(kThreads, MINB) k_scan(const __grid_constant__
     const uint32_t seg_len = p.segs[p.blocks[p.block_begin].x].len_bytes;
     const uint32_t m = min(p.qlen_bytes, seg_len);               // bytes compared
     const uint32_t mask_last = (m & 3u) ? ((1u << (8u * (m & 3u))) - 1u) : 0xffffffffu;
-    const uint16_t* hrow = p.hmax_tab + (size_t)m * p.R;
+    const uint16_t* hrow = s_hrow;
     for (uint32_t i = tid; i < 257; i += kThreads) s_rank[i] = p.rank_tab[m * 257 + i];
+    for (uint32_t i = tid; i < p.R; i += kThreads) s_hrow[i] = p.hmax_tab[(size_t)m * p.R + i];
+    __syncthreads();
 
     const uint64_t n_blocks = p.block_end - p.block_begin;
     const uint32_t my_lo = p.block_begin + (uint32_t)(n_blocks * blockIdx.x / gridDim.x);
