@@ -550,9 +550,9 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
         if (s->profiling) CU(cudaEventRecord(s->tile_events[3 * ti], s->stream));
         // threshold bootstrap from a stratified row sample (no emission), then one launch per compared length
         if (n_blocks_total > 0) {
-            // batches: 256 blocks (cost ~ T*256K pairs, negligible); small tiles: ~1 % of the store, because
+            // batches: 64 blocks, refined by the two warm-up ranges below; small tiles: ~1 % of the store, because
             // their threshold feedback is slow relative to the scan (the first items of all CTAs run at once)
-            uint32_t want = T >= 64 ? 256 : std::min<uint32_t>(1024, std::max<uint32_t>(64, n_blocks_total / 128));
+            uint32_t want = T >= 64 ? 64 : std::min<uint32_t>(1024, std::max<uint32_t>(64, n_blocks_total / 128));
             want = std::max<uint32_t>(want, (4 * k + kBlockRows - 1) / kBlockRows);
             SampleParams sp{};
             uint32_t total = 0;
@@ -572,7 +572,18 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
             st.kernel_launches += 2;
         }
         const uint32_t bpi_main = T >= 64 ? 4 : (T >= 8 ? 8 : 16);
-        if ((rc = scan_range(s, p, 0, n_blocks_total, bpi_main))) return rc;
+        // Batches: the first wave of the bulk launch covers ~1.8 M rows before any threshold feedback, so the
+        // threshold is first tightened on two short ranges (64 and 512 blocks) that are split over query
+        // sub-tiles (gridDim.y) to fill the chip; every range is scanned exactly once.
+        uint32_t done = 0;
+        if (T >= 64) {
+            for (uint32_t span : {64u, 512u}) {
+                if (n_blocks_total - done <= span * 4) break;
+                if ((rc = scan_range(s, p, done, done + span, bpi_main))) return rc;
+                done += span;
+            }
+        }
+        if ((rc = scan_range(s, p, done, n_blocks_total, bpi_main))) return rc;
         if (s->profiling) CU(cudaEventRecord(s->tile_events[3 * ti + 1], s->stream));
 
         SelectParams sp = make_select(t, p);

@@ -223,10 +223,11 @@ __global__ void __launch_bounds__(kThreads, MINB) k_scan(const __grid_constant__
 
     // item size ramps G, 2G, 4G .. blocks_per_item: the first bounds a CTA works with are the loosest
     uint32_t item_blocks = p.update_tau ? G : p.blocks_per_item;
-    for (uint32_t b_lo = my_lo; b_lo < my_hi;) {
+    uint32_t n_items_done = 0;
+    for (uint32_t b_lo = my_lo; b_lo < my_hi; n_items_done++) {
         const uint32_t b_hi = min(b_lo + item_blocks, my_hi);
         __syncthreads();  // previous item's readers of hm are done
-        if (prefetch && item_blocks == p.blocks_per_item) {   // steady state: bound fetched during the previous item
+        if (prefetch && n_items_done >= 3) {                  // steady state: bound fetched during the previous item
             if (tid < T) hm[tid] = hm_next;
         } else {                                              // ramp-up items: always the freshest bound
             for (uint32_t q = tid; q < T; q += kThreads) hm[q] = hrow[__ldcg(&p.tau[q0 + q])];
