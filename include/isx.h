@@ -159,6 +159,23 @@ int isx_merge_device(isx_store_t* s, uint32_t n_shards, size_t q, uint32_t k, si
 int isx_match_all(isx_store_t* s, const uint8_t* query, uint32_t qlen, uint32_t thr_num, uint32_t thr_den, size_t max_out,
                   void* keys_out, uint16_t* hamming_out, uint16_t* nbits_out, uint64_t* total_out);
 
+/*
+ * Cross-rank threshold sharing for row-sharded search (one process per GPU, all GPUs on one NVLink box).
+ * Every rank owns "home" rank-histograms for a slice of the queries of a batch; peers map them through
+ * CUDA IPC and (a) count every candidate they emit there with remote atomics, (b) tighten their thresholds
+ * from those GLOBAL counts. A shard then stops emitting rows that cannot reach the merged top-k, which keeps
+ * the per-shard work proportional to its rows. Results are unchanged (the merged top-k is exact either way).
+ *   isx_share_init   allocate + export this rank's histograms (handle_out: 64 bytes, cudaIpcMemHandle_t)
+ *   isx_share_attach map a peer's histograms (handle from its isx_share_init)
+ *   isx_share_reset  enqueue zeroing of the home histograms on the store's stream. Protocol per batch, same on
+ *                    every rank: isx_share_reset -> a collective on the same stream (barrier) ->
+ *                    isx_search_device (identical queries, qlens, k on all ranks) -> all-gather + isx_merge_device.
+ * Sharing is used only when all of world > 1, q <= max_queries and the distance classes fit (<= 512 ranks).
+ */
+int isx_share_init(isx_store_t* s, uint32_t world, uint32_t rank, uint32_t max_queries, void* handle_out);
+int isx_share_attach(isx_store_t* s, uint32_t peer_rank, const void* handle);
+int isx_share_reset(isx_store_t* s);
+
 /* largest k isx_search accepts for this store (shared-memory bound of the final selection) */
 int isx_max_k(isx_store_t* s, uint32_t* k_out);
 

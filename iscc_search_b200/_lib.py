@@ -50,7 +50,8 @@ SYMBOLS = (
     "isx_last_error", "isx_abi_version", "isx_device_count", "isx_open", "isx_close", "isx_set_stream",
     "isx_set_profiling", "isx_get_stats", "isx_add", "isx_remove", "isx_contains", "isx_get", "isx_size",
     "isx_clear", "isx_device_bytes", "isx_length_mask", "isx_save", "isx_load", "isx_search",
-    "isx_search_device", "isx_merge_device", "isx_max_k", "isx_match_all",
+    "isx_search_device", "isx_merge_device", "isx_max_k", "isx_match_all", "isx_share_init", "isx_share_attach",
+    "isx_share_reset",
 )
 
 
@@ -104,6 +105,9 @@ def lib():
     L.isx_merge_device.argtypes = [vp, u32, sz, u32, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci]
     L.isx_max_k.argtypes = [vp, P(u32)]
     L.isx_match_all.argtypes = [vp, vp, u32, u32, u32, sz, vp, vp, vp, P(u64)]
+    L.isx_share_init.argtypes = [vp, u32, u32, u32, vp]
+    L.isx_share_attach.argtypes = [vp, u32, vp]
+    L.isx_share_reset.argtypes = [vp]
     for name in SYMBOLS:
         if name != "isx_last_error":
             getattr(L, name).restype = ci

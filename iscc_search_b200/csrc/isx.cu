@@ -140,6 +140,13 @@ struct isx_store {
 
     RankTables tables;
 
+    // cross-rank threshold sharing (see ScanParams::g_hist)
+    uint32_t share_world = 0, share_rank = 0, share_maxq = 0;
+    static constexpr uint32_t kShareRcap = 512;   // ranks per query in the shared histograms (385 for 64..256-bit codes)
+    uint32_t* share_local = nullptr;              // this rank's home histograms (cudaMalloc, IPC exported)
+    uint32_t* share_ptrs[kMaxRanks] = {nullptr};  // [r] = rank r's home histograms mapped into this process
+    size_t share_bytes = 0;
+
     // scratch
     DevBuf d_stage_codes, d_stage_keys, d_stage_dest, d_moves;
     DevBuf d_queries, d_tau, d_hist, d_shist, d_cnt, d_ovf, d_cand, d_qmap, d_fb, d_fb_cand;
@@ -503,6 +510,8 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
             s->tile_events.push_back(e);
         }
 
+    // shared (cross-rank) histograms need every rank to see the same query batch in the same order
+    const bool share_on = s->share_world > 1 && R <= isx_store::kShareRcap && Q <= s->share_maxq;
     auto make_params = [&](const Tile& t) {
         ScanParams p{};
         p.segs = s->d_segs.as<SegDesc>();
@@ -519,6 +528,12 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
         p.rank_tab = tb.d_rank.as<uint16_t>();
         p.hmax_tab = tb.d_hmax.as<uint16_t>();
         p.update_tau = 1;
+        if (share_on) {
+            for (uint32_t r = 0; r < s->share_world; r++) p.g_hist[r] = s->share_ptrs[r];
+            p.g_world = s->share_world;
+            p.g_rcap = isx_store::kShareRcap;
+            p.g_q0 = (uint32_t)t.t0;
+        }
         return p;
     };
     auto make_select = [&](const Tile& t, const ScanParams& p) {
@@ -616,34 +631,44 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
             if (!hf_ovf[t.t0 + qi]) continue;
             st.fallback_queries++;
             const uint32_t dstar = hf_info[2 * (t.t0 + qi)], count_le = hf_info[2 * (t.t0 + qi) + 1];
-            const size_t C2 = (size_t)count_le + 1024;
-            if (s->d_fb_cand.ensure(C2 * 8)) return ISX_ENOMEM;
-            ScanParams p2 = make_params(t);
-            p2.queries += (size_t)qi * 8;
-            p2.T = 1;
-            p2.cand = s->d_fb_cand.as<uint64_t>();
-            p2.C = (uint32_t)std::min<size_t>(C2, 0xffffffffu);
-            p2.update_tau = 0;
-            k_init_queries<<<std::max<uint32_t>(1, (R + 255) / 256), 256, 0, s->stream>>>(p2.tau, p2.hist, nullptr, p2.cand_cnt, p2.overflow, 1, R, dstar);
-            CU(cudaGetLastError());
-            st.kernel_launches++;
-            if (s->profiling) CU(cudaEventRecord(s->ev[1], s->stream));
-            if ((rc = scan_range(s, p2, 0, n_blocks_total, 16))) return rc;
-            if (s->profiling) CU(cudaEventRecord(s->ev[2], s->stream));
-            SelectParams sp2 = make_select(t, p2);
-            sp2.cand = p2.cand; sp2.C = p2.C; sp2.T = 1; sp2.qmap += qi; sp2.tau_init = dstar;
-            sp2.skip_overflowed = 0;
-            k_select<<<1, kSelectThreads, sel_smem, s->stream>>>(sp2);
-            CU(cudaGetLastError());
-            st.kernel_launches++;
-            if (s->profiling) CU(cudaEventRecord(s->ev[3], s->stream));
-            CU(cudaStreamSynchronize(s->stream));
-            if (s->profiling) {
-                float a = 0, b = 0;
-                CU(cudaEventElapsedTime(&a, s->ev[1], s->ev[2]));
-                CU(cudaEventElapsedTime(&b, s->ev[2], s->ev[3]));
-                st.scan_ms += a;
-                st.select_ms += b;
+            // With shared thresholds the local histogram may under-count beyond the final global threshold, so the
+            // buffer size is a first guess: the re-scan is repeated with a doubled buffer until nothing is dropped.
+            size_t C2 = (size_t)count_le + 1024;
+            for (;;) {
+                if (s->d_fb_cand.ensure(C2 * 8)) return ISX_ENOMEM;
+                ScanParams p2 = make_params(t);
+                p2.queries += (size_t)qi * 8;
+                p2.T = 1;
+                p2.cand = s->d_fb_cand.as<uint64_t>();
+                p2.C = (uint32_t)std::min<size_t>(C2, 0xffffffffu);
+                p2.update_tau = 0;
+                p2.g_world = 0;  // local, fixed threshold
+                k_init_queries<<<std::max<uint32_t>(1, (R + 255) / 256), 256, 0, s->stream>>>(p2.tau, p2.hist, nullptr, p2.cand_cnt, p2.overflow, 1, R, dstar);
+                CU(cudaGetLastError());
+                st.kernel_launches++;
+                if (s->profiling) CU(cudaEventRecord(s->ev[1], s->stream));
+                if ((rc = scan_range(s, p2, 0, n_blocks_total, 16))) return rc;
+                if (s->profiling) CU(cudaEventRecord(s->ev[2], s->stream));
+                SelectParams sp2 = make_select(t, p2);
+                sp2.cand = p2.cand; sp2.C = p2.C; sp2.T = 1; sp2.qmap += qi; sp2.tau_init = dstar;
+                sp2.skip_overflowed = 1;  // a still-too-small buffer is reported, not silently truncated
+                k_select<<<1, kSelectThreads, sel_smem, s->stream>>>(sp2);
+                CU(cudaGetLastError());
+                st.kernel_launches++;
+                if (s->profiling) CU(cudaEventRecord(s->ev[3], s->stream));
+                uint32_t again = 0, seen = 0;
+                CU(cudaMemcpyAsync(&again, p2.overflow, 4, cudaMemcpyDeviceToHost, s->stream));
+                CU(cudaMemcpyAsync(&seen, p2.cand_cnt, 4, cudaMemcpyDeviceToHost, s->stream));
+                CU(cudaStreamSynchronize(s->stream));
+                if (s->profiling) {
+                    float a = 0, b = 0;
+                    CU(cudaEventElapsedTime(&a, s->ev[1], s->ev[2]));
+                    CU(cudaEventElapsedTime(&b, s->ev[2], s->ev[3]));
+                    st.scan_ms += a;
+                    st.select_ms += b;
+                }
+                if (!again) break;
+                C2 = (size_t)seen + 1024;
             }
         }
     }
@@ -735,6 +760,9 @@ int isx_close(isx_store_t* s) {
     for (DevBuf* b : bufs) b->release();
     PinnedBuf* pbufs[] = {&s->h_queries, &s->h_qmap, &s->h_flags, &s->h_out};
     for (PinnedBuf* b : pbufs) b->release();
+    for (uint32_t r = 0; r < s->share_world; r++)
+        if (r != s->share_rank && s->share_ptrs[r]) cudaIpcCloseMemHandle(s->share_ptrs[r]);
+    if (s->share_local) cudaFree(s->share_local);
     for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : s->tile_events) cudaEventDestroy(ev);
     for (int i = 0; i < 3; i++) { if (s->side[i]) cudaStreamDestroy(s->side[i]); if (s->join_ev[i]) cudaEventDestroy(s->join_ev[i]); }
@@ -1114,6 +1142,57 @@ int isx_match_all(isx_store_t* s, const uint8_t* query, uint32_t qlen, uint32_t 
     CU(cudaStreamSynchronize(s->stream));
     if (s->key_bytes == 8) memcpy(keys_out, khi.data(), (size_t)n * 8);
     else for (uint32_t i = 0; i < n; i++) store_key(s, keys_out, i, khi[i], klo[i]);
+    return 0;
+}
+
+// ---- cross-rank threshold sharing over NVLink peer memory (CUDA IPC) -------------------------------------
+int isx_share_init(isx_store_t* s, uint32_t world, uint32_t rank, uint32_t max_queries, void* handle_out) {
+    if (!s || !handle_out) return fail(ISX_EINVAL, "NULL argument");
+    if (world < 2 || world > (uint32_t)kMaxRanks || rank >= world) return fail(ISX_EINVAL, "world must be 2..%d and rank < world", kMaxRanks);
+    if (max_queries == 0) return fail(ISX_EINVAL, "max_queries must be > 0");
+    std::lock_guard<std::mutex> gw(s->work_mu);
+    int rc = set_device(s);
+    if (rc) return rc;
+    if (s->share_local) return fail(ISX_EINVAL, "sharing is already initialised for this store");
+    const size_t slots = (max_queries + world - 1) / world;
+    s->share_bytes = slots * isx_store::kShareRcap * sizeof(uint32_t);
+    CU(cudaMalloc(&s->share_local, s->share_bytes));
+    CU(cudaMemset(s->share_local, 0, s->share_bytes));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s->share_local));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handle_out, &h, sizeof h);
+    s->share_world = world;
+    s->share_rank = rank;
+    s->share_maxq = max_queries;
+    s->share_ptrs[rank] = s->share_local;
+    return 0;
+}
+
+int isx_share_attach(isx_store_t* s, uint32_t peer_rank, const void* handle) {
+    if (!s || !handle) return fail(ISX_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> gw(s->work_mu);
+    if (!s->share_local) return fail(ISX_EINVAL, "call isx_share_init first");
+    if (peer_rank >= s->share_world || peer_rank == s->share_rank) return fail(ISX_EINVAL, "bad peer rank %u", peer_rank);
+    int rc = set_device(s);
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    s->share_ptrs[peer_rank] = reinterpret_cast<uint32_t*>(p);
+    return 0;
+}
+
+int isx_share_reset(isx_store_t* s) {
+    if (!s) return fail(ISX_EINVAL, "store is NULL");
+    std::lock_guard<std::mutex> gw(s->work_mu);
+    if (!s->share_local) return 0;
+    int rc = set_device(s);
+    if (rc) return rc;
+    for (uint32_t r = 0; r < s->share_world; r++)
+        if (!s->share_ptrs[r]) return fail(ISX_EINVAL, "peer %u is not attached", r);
+    CU(cudaMemsetAsync(s->share_local, 0, s->share_bytes, s->stream));
     return 0;
 }
 

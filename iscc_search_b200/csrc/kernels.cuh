@@ -30,6 +30,7 @@ constexpr uint32_t kRowBits = 22;      // rows per segment <= 4 Mi
 constexpr uint32_t kSegBits = 16;      // segments per store <= 65536
 constexpr uint32_t kHBits = 9;         // hamming <= 256
 constexpr uint32_t kRankBits = 13;     // dense ranks < 8192
+constexpr int kMaxRanks = 8;           // GPUs of one box sharing thresholds through peer memory
 
 struct SegDesc {
     uint32_t* planes;   // [words][cap]
@@ -60,6 +61,13 @@ struct ScanParams {
     uint32_t update_tau;         // 0: fixed threshold (exact re-scan)
     uint32_t q_split;            // queries per CTA along gridDim.y (small ranges are split over queries
                                  // so the bootstrap rounds still fill the chip)
+    // Cross-rank threshold sharing (multi-GPU): rank histograms of ALL ranks are summed in peer memory
+    // over NVLink (CUDA IPC mapped). Query gq = g_q0 + q lives on rank gq % g_world, slot gq / g_world.
+    // Every emission is also counted there (fire-and-forget remote RED); thresholds are tightened from the
+    // global counts, i.e. against k rows found ANYWHERE, so a shard stops emitting rows that cannot reach
+    // the merged top-k. g_world == 0: disabled (single GPU / emulated shards).
+    uint32_t* g_hist[kMaxRanks];
+    uint32_t g_world, g_rcap, g_q0;
 };
 
 __device__ __forceinline__ uint64_t pack_cand(uint32_t rank, uint32_t h, uint32_t seg, uint32_t row) {
@@ -100,6 +108,10 @@ __device__ __noinline__ void emit_group(const ScanParams& p, uint32_t q, uint32_
         if (e) {
             const uint32_t rank = s_rank[d[r]];
             atomicAdd(&p.hist[(size_t)q * p.R + rank], 1u);
+            if (p.g_world) {
+                const uint32_t gq = p.g_q0 + q;
+                atomicAdd(&p.g_hist[gq % p.g_world][(size_t)(gq / p.g_world) * p.g_rcap + rank], 1u);  // NVLink RED
+            }
             const uint32_t slot = base + __popc(bal & ((1u << lane) - 1u));
             if (slot < p.C) p.cand[(size_t)q * p.C + slot] = pack_cand(rank, d[r], seg, row0 + r);
             else p.overflow[q] = 1u;
@@ -110,13 +122,21 @@ __device__ __noinline__ void emit_group(const ScanParams& p, uint32_t q, uint32_
 
 // Tighten tau[q] to the smallest rank t with (observed) sum_{r<=t} hist[q][r] >= k. Observed counts
 // only under-count, so t is always >= the true k-th rank. One warp per query.
+__device__ __forceinline__ uint32_t ld_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p));  // peer memory: never a stale L1 line
+    return v;
+}
+
 __device__ __forceinline__ void tighten_tau(const ScanParams& p, uint32_t q, uint32_t lane) {
     uint32_t tcur = __ldcg(&p.tau[q]);
-    const uint32_t* hq = p.hist + (size_t)q * p.R;
+    const bool shared = p.g_world != 0;
+    const uint32_t gq = p.g_q0 + q;
+    const uint32_t* hq = shared ? p.g_hist[gq % p.g_world] + (size_t)(gq / p.g_world) * p.g_rcap : p.hist + (size_t)q * p.R;
     uint32_t cum = 0;
     for (uint32_t base = 0; base <= tcur; base += 32) {
         uint32_t r = base + lane;
-        uint32_t v = (r <= tcur) ? __ldcg(&hq[r]) : 0u;
+        uint32_t v = (r <= tcur) ? (shared ? ld_sys(&hq[r]) : __ldcg(&hq[r])) : 0u;
         uint32_t incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {

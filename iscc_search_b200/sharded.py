@@ -36,7 +36,7 @@ def record_layout(q, k):
 class ShardedSearcher:
     """Search front of one rank's store; `search` is a collective call (all ranks, same arguments)."""
 
-    def __init__(self, store, rank=0, world=1, group=None, device=None):
+    def __init__(self, store, rank=0, world=1, group=None, device=None, share_thresholds=True, max_queries=16384):
         import torch
 
         self.torch = torch
@@ -44,6 +44,26 @@ class ShardedSearcher:
         self.rank, self.world, self.group = rank, world, group
         self.device = torch.device("cuda", store.device) if device is None else device
         self._bufs = {}
+        self.shared = False
+        if world > 1 and share_thresholds:
+            self._init_sharing(max_queries)
+
+    def _init_sharing(self, max_queries):
+        """Exchange CUDA IPC handles of the per-rank home histograms (include/isx.h: isx_share_*), all ranks call this."""
+        torch, dist = self.torch, self.torch.distributed
+        handle = (ctypes.c_ubyte * 64)()
+        _lib.check(_lib.lib().isx_share_init(self.store.handle, self.world, self.rank, max_queries, handle))
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+        every = torch.empty(64 * self.world, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(every, mine, group=self.group)
+        every = every.cpu().numpy()
+        for r in range(self.world):
+            if r != self.rank:
+                peer = (ctypes.c_ubyte * 64)(*every[64 * r: 64 * (r + 1)].tolist())
+                _lib.check(_lib.lib().isx_share_attach(self.store.handle, r, peer))
+        self._token = torch.zeros(1, dtype=torch.int32, device=self.device)
+        dist.barrier(group=self.group)
+        self.shared = True
 
     def _buf(self, name, nbytes):
         t = self._bufs.get(name)
@@ -66,6 +86,11 @@ class ShardedSearcher:
         tn, td = (0, 0) if thr is None else thr
         L = _lib.lib()
         self.store.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        if self.shared:
+            # zero the home histograms, then a collective on the same stream: no rank starts emitting before every
+            # rank has zeroed (the all-gather at the end of the previous batch already fenced its emissions)
+            _lib.check(L.isx_share_reset(self.store.handle))
+            self.torch.distributed.all_reduce(self._token, group=self.group)
         _lib.check(L.isx_search_device(self.store.handle, d_queries.data_ptr(), 1, _lib.ptr(qlens), q, k, tn, td,
                                        base + off["khi"], base + off["klo"], base + off["h"], base + off["n"],
                                        base + off["cnt"], 0))

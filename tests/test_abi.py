@@ -65,3 +65,11 @@ def test_argument_validation_happens_before_any_device_work():
     assert b"key_bytes" in L.isx_last_error()
     assert L.isx_open(ctypes.byref(h), 0, 8, 40, 0) == _lib.ISX_EINVAL
     assert L.isx_open(ctypes.byref(h), 0, 8, 16, 32) == _lib.ISX_EINVAL
+
+
+def test_share_api_validates_arguments():
+    L = _lib.lib()
+    buf = (ctypes.c_ubyte * 64)()
+    assert L.isx_share_init(None, 2, 0, 16, buf) == _lib.ISX_EINVAL
+    assert L.isx_share_attach(None, 1, buf) == _lib.ISX_EINVAL
+    assert L.isx_share_reset(None) == _lib.ISX_EINVAL
