@@ -31,9 +31,15 @@ if args.backend == "nccl":
     sel = owner_of(keys, world) == rank
     st = _lib.Store(device=rank, key_bytes=8, max_bytes=32)
     st.add(np.ascontiguousarray(keys[sel]), np.ascontiguousarray(codes[sel]), np.ascontiguousarray(lens[sel]))
-    gk, gh, gn, gc = ShardedSearcher(st, rank, world, None, torch.device("cuda", rank)).search(queries, qlens, k)
+    searcher = ShardedSearcher(st, rank, world, None, torch.device("cuda", rank))
+    gk, gh, gn, gc = (a.copy() for a in searcher.search(queries, qlens, k))
+    # a second batch right behind the first: different query order, exercises the reset -> barrier -> search protocol
+    perm = np.random.default_rng(7).permutation(q)
+    gk2, gh2, gn2, gc2 = (a.copy() for a in searcher.search(np.ascontiguousarray(queries[perm]), np.ascontiguousarray(qlens[perm]), k))
+    inv = np.argsort(perm)
     if rank == 0:
-        np.savez(args.out, keys=gk, h=gh, nb=gn, cnt=gc, n=n, q=q, k=k)
+        np.savez(args.out, keys=gk, h=gh, nb=gn, cnt=gc, keys2=gk2[inv], h2=gh2[inv], nb2=gn2[inv], cnt2=gc2[inv], n=n, q=q, k=k,
+                 shared=searcher.shared)
     dist.barrier()
     dist.destroy_process_group()
 else:

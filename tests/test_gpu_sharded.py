@@ -109,17 +109,21 @@ def _n_gpus():
     return n.value if _lib.lib().isx_device_count(ctypes.byref(n)) == 0 else 0
 
 
-def test_two_rank_nccl_search_equals_oracle(cuda, tmp_path):
-    if _n_gpus() < 2:
-        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_rank_nccl_search_with_shared_thresholds_equals_oracle(cuda, tmp_path, world):
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs (run with gpurun --gpus {world})")
     out = tmp_path / "result.npz"
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", str(ROOT / "tests" / "sharded_worker.py"), "--backend", "nccl", "--out", str(out)]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29533 + world), str(ROOT / "tests" / "sharded_worker.py"), "--backend", "nccl", "--out", str(out)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(ROOT), env=dict(os.environ))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     d = np.load(out)
     n, q, k = int(d["n"]), int(d["q"]), int(d["k"])
+    assert bool(d["shared"]), "threshold sharing over peer memory was not active"
     keys, codes, lens = make_store_arrays(n, 31)
     queries, qlens = synth.make_queries(q, n, 32, 31)
     rows, h, nb, cnt = oracle_topk(keys, codes, lens, queries, qlens, k)
+    # two batches were searched back to back (reset/fence protocol of the shared histograms): both must be exact
     assert_same_topk(d["keys"], d["h"], d["nb"], d["cnt"], keys, rows, h, nb, cnt)
+    assert_same_topk(d["keys2"], d["h2"], d["nb2"], d["cnt2"], keys, rows, h, nb, cnt)
