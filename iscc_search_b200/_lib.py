@@ -254,7 +254,16 @@ class Store:
             max_out = int(total.value) + 1024
 
     def set_stream(self, cuda_stream):
-        check(lib().isx_set_stream(self.handle, ctypes.c_void_p(cuda_stream) if cuda_stream else None))
+        """
+        Run all work of this store on the given CUDA stream handle (e.g. `torch.cuda.current_stream().cuda_stream`).
+        torch's default stream has handle 0, which the C ABI reads as "use the store's own stream"; it is passed as
+        cudaStreamLegacy (0x1) so that the store really shares torch's stream and stays ordered with its collectives.
+        `None` restores the store's own non-blocking stream.
+        """
+        if cuda_stream is None:
+            check(lib().isx_set_stream(self.handle, None))
+        else:
+            check(lib().isx_set_stream(self.handle, ctypes.c_void_p(cuda_stream if cuda_stream else 1)))
 
     def set_profiling(self, enabled):
         check(lib().isx_set_profiling(self.handle, 1 if enabled else 0))
