@@ -254,10 +254,10 @@ def main():
         return res, store.stats()
 
     # ---- warm-up, then K timed steps (device-resident inputs). The store (2 GB) is far larger than L2. ----
+    sampler = ClockSampler(local_rank)  # started before the warm-up: nvidia-smi needs ~0.5 s before its first sample
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_device()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches, scan_ms, algo_popc, issued_popc, pairs, cands, fallbacks = 0, 0.0, 0, 0, 0, 0, 0
