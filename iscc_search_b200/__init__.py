@@ -8,6 +8,7 @@ All search arithmetic runs in libisx_b200.so (hand-written sm_100a CUDA); there 
 
 from iscc_search_b200.matches import BatchMatches, Match, Matches  # noqa: F401
 from iscc_search_b200.nphd import ShardedIndex128, ShardedNphdIndex  # noqa: F401
+from iscc_search_b200.utils import timer  # noqa: F401
 
-__all__ = ["ShardedNphdIndex", "ShardedIndex128", "Matches", "BatchMatches", "Match"]
+__all__ = ["ShardedNphdIndex", "ShardedIndex128", "Matches", "BatchMatches", "Match", "timer"]
 __version__ = "0.1.0"

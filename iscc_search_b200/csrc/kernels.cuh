@@ -483,10 +483,6 @@ __global__ void __launch_bounds__(kSelectThreads) k_select(const SelectParams p)
     const uint32_t q = blockIdx.x;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t oq = p.qmap[q];
-    if (p.skip_overflowed && p.overflow[q]) {
-        // hist is still exact up to the final tau: report d* and count_le so the host can re-scan.
-        // (computed below, then we bail out before touching the truncated candidate list)
-    }
     const uint32_t* hq = p.hist + (size_t)q * p.R;
     const uint32_t n_list = min(p.cand_cnt[q], p.C);
 
@@ -533,6 +529,8 @@ __global__ void __launch_bounds__(kSelectThreads) k_select(const SelectParams p)
     const uint32_t n_out = min(p.k, total_le);
 
     if (p.skip_overflowed && p.overflow[q]) {
+        // candidate list truncated: the histogram still gives d* and the number of rows within it, which is
+        // what the host needs to size the exact re-scan of this query
         if (tid == 0) { p.fallback_info[2 * q] = dstar; p.fallback_info[2 * q + 1] = total_le; p.out_cnt[oq] = 0; }
         return;
     }

@@ -84,3 +84,60 @@ def test_threshold_mode(cuda):
 def test_many_queries_multiple_tiles(cuda):
     # more queries than one shared-memory tile (2048)
     _run(n=30_000, q=4500, k=5, seed=606, lengths=(8, 32), qlengths=(8, 32))
+
+
+def test_empty_query_batch_and_empty_store(cuda):
+    st = Store(key_bytes=8, max_bytes=32)
+    try:
+        gk, gh, gn, gc, _ = st.search(np.zeros((0, 32), np.uint8), np.zeros(0, np.uint8), 5)
+        assert gk.shape == (0, 5) and gc.shape == (0,)
+        q, ql = synth.make_queries(3, 0, 1)
+        gk, gh, gn, gc, _ = st.search(q, ql, 5)          # empty store: zero results per query
+        assert (gc == 0).all()
+        with pytest.raises(ValueError):
+            st.search(q, np.array([0, 8, 8], dtype=np.uint8), 5)   # zero-length query
+        with pytest.raises(ValueError):
+            st.search(q, np.array([33, 8, 8], dtype=np.uint8), 5)  # longer than max_bytes
+    finally:
+        st.close()
+
+
+def test_k_at_the_supported_maximum_with_128bit_keys_and_heavy_ties(cuda):
+    # k = isx_max_k (4096 for 128-bit keys), 64-bit codes with only 65 distinct distances: the cut-off tie group is
+    # far larger than the shared-memory sort capacity -> radix select on the 16-byte keys
+    n = 60_000
+    rng = np.random.default_rng(12)
+    codes = np.zeros((n, 32), dtype=np.uint8)
+    codes[:, :8] = rng.integers(0, 256, size=(n, 8), dtype=np.uint8)
+    lens = np.full(n, 8, dtype=np.uint8)
+    hi = rng.integers(0, 2**20, size=n, dtype=np.uint64)      # many equal high halves: order decided by the low half
+    lo = rng.permutation(n).astype(np.uint64)
+    keys = np.zeros((n, 16), dtype=np.uint8)
+    keys[:, :8] = hi.astype(">u8").view(np.uint8).reshape(n, 8)
+    keys[:, 8:] = lo.astype(">u8").view(np.uint8).reshape(n, 8)
+    st = Store(key_bytes=16, max_bytes=8, fixed_len=8)
+    try:
+        st.add(keys, codes, lens)
+        k = st.max_k()
+        q, ql = codes[:3].copy(), lens[:3].copy()
+        gk, gh, gn, gc, _ = st.search(q, ql, k)
+        rows, h, nb, cnt = oracle_topk(hi, codes, lens, q, ql, k, keys_lo=lo)
+        assert_same_topk(gk, gh, gn, gc, hi, rows, h, nb, cnt, keys_lo=lo)
+    finally:
+        st.close()
+
+
+def test_byte_granular_lengths_with_threshold_and_codes_out(cuda):
+    n = 15_000
+    keys, codes, lens = make_store_arrays(n, 77, (3, 7, 8, 11, 32))
+    queries, qlens = synth.make_queries(20, n, 78, 77, (3, 8, 11, 30), (3, 7, 8, 11, 32))
+    st = Store(key_bytes=8, max_bytes=32)
+    try:
+        st.add(keys, codes, lens)
+        gk, gh, gn, gc, gcodes = st.search(queries, qlens, 30, (1, 8), True)
+        rows, h, nb, cnt = oracle_topk(keys, codes, lens, queries, qlens, 30, (1, 8))
+        assert_same_topk(gk, gh, gn, gc, keys, rows, h, nb, cnt)
+        for i in range(len(qlens)):
+            assert np.array_equal(gcodes[i, : cnt[i]], codes[rows[i, : cnt[i]]])     # matched stored codes, zero padded
+    finally:
+        st.close()
