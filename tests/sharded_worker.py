@@ -37,6 +37,21 @@ if args.backend == "nccl":
     perm = np.random.default_rng(7).permutation(q)
     gk2, gh2, gn2, gc2 = (a.copy() for a in searcher.search(np.ascontiguousarray(queries[perm]), np.ascontiguousarray(qlens[perm]), k))
     inv = np.argsort(perm)
+    # third batch: 150K extra rows sharing ONE code -> every rank's candidate buffer overflows for that query and the
+    # exact re-scan path runs while thresholds are shared; the merged result must be the 100 smallest keys among the ties
+    dup_n = 150_000
+    dup_keys = synth.make_keys(10**9, dup_n, 77)
+    dup_codes = np.zeros((dup_n, 32), dtype=np.uint8)
+    dup_codes[:, :16] = 0xA7
+    dup_lens = np.full(dup_n, 16, dtype=np.uint8)
+    dsel = owner_of(dup_keys, world) == rank
+    st.add(np.ascontiguousarray(dup_keys[dsel]), np.ascontiguousarray(dup_codes[dsel]), np.ascontiguousarray(dup_lens[dsel]))
+    q3 = np.concatenate([dup_codes[:1], queries[:7]])
+    ql3 = np.concatenate([dup_lens[:1], qlens[:7]])
+    gk3, gh3, gn3, gc3 = (a.copy() for a in searcher.search(q3, ql3, k))
+    fb = st.stats()["fallback_queries"]
+    if rank == 0:
+        np.savez(args.out.replace(".npz", "_dup.npz"), keys=gk3, h=gh3, nb=gn3, cnt=gc3, fallback=fb, dup_n=dup_n)
     if rank == 0:
         np.savez(args.out, keys=gk, h=gh, nb=gn, cnt=gc, keys2=gk2[inv], h2=gh2[inv], nb2=gn2[inv], cnt2=gc2[inv], n=n, q=q, k=k,
                  shared=searcher.shared)

@@ -127,3 +127,17 @@ def test_multi_rank_nccl_search_with_shared_thresholds_equals_oracle(cuda, tmp_p
     # two batches were searched back to back (reset/fence protocol of the shared histograms): both must be exact
     assert_same_topk(d["keys"], d["h"], d["nb"], d["cnt"], keys, rows, h, nb, cnt)
     assert_same_topk(d["keys2"], d["h2"], d["nb2"], d["cnt2"], keys, rows, h, nb, cnt)
+    # third batch: mass duplicates -> candidate overflow + exact re-scan on every rank, thresholds still shared
+    dd = np.load(str(out).replace(".npz", "_dup.npz"))
+    dup_n = int(dd["dup_n"])
+    assert int(dd["fallback"]) >= 1
+    dup_keys = synth.make_keys(10**9, dup_n, 77)
+    dup_codes = np.zeros((dup_n, 32), dtype=np.uint8)
+    dup_codes[:, :16] = 0xA7
+    all_keys = np.concatenate([keys, dup_keys])
+    all_codes = np.concatenate([codes, dup_codes])
+    all_lens = np.concatenate([lens, np.full(dup_n, 16, dtype=np.uint8)])
+    q3 = np.concatenate([dup_codes[:1], queries[:7]])
+    ql3 = np.concatenate([np.array([16], dtype=np.uint8), qlens[:7]])
+    rows3, h3, nb3, cnt3 = oracle_topk(all_keys, all_codes, all_lens, q3, ql3, k)
+    assert_same_topk(dd["keys"], dd["h"], dd["nb"], dd["cnt"], all_keys, rows3, h3, nb3, cnt3)
