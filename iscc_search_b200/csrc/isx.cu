@@ -44,6 +44,7 @@ static int fail(int code, const char* fmt, ...) {
 constexpr uint32_t kMinSegRows = 4096;
 constexpr uint32_t kMaxSegRows = 1u << kRowBits;  // 4 Mi rows
 constexpr uint32_t kBlockRows = kRowsPerStep;     // 1024
+constexpr uint32_t kMaxK = 65536;                 // beyond the shared-memory sort capacity winners are sorted in global scratch
 
 // growable device buffer
 struct DevBuf {
@@ -150,7 +151,7 @@ struct isx_store {
     // scratch
     DevBuf d_stage_codes, d_stage_keys, d_stage_dest, d_moves;
     DevBuf d_queries, d_tau, d_hist, d_shist, d_cnt, d_ovf, d_cand, d_qmap, d_fb, d_fb_cand;
-    DevBuf d_out_khi, d_out_klo, d_out_h, d_out_n, d_out_cnt, d_out_codes;
+    DevBuf d_out_khi, d_out_klo, d_out_h, d_out_n, d_out_cnt, d_out_codes, d_bigsort;
     PinnedBuf h_queries, h_qmap, h_flags, h_out;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> tile_events;  // 3 per tile, grown on demand (profiling only)
@@ -399,7 +400,7 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
     if (k < 1) return fail(ISX_EINVAL, "`count` must be >= 1");
     const uint32_t key_words = s->key_bytes == 16 ? 2 : 1;
     const uint32_t cap_max = max_sort_cap(s);
-    if (k > cap_max) return fail(ISX_ELIMIT, "count %u exceeds the supported maximum %u", k, cap_max);
+    if (k > kMaxK) return fail(ISX_ELIMIT, "count %u exceeds the supported maximum %u", k, kMaxK);
     for (size_t i = 0; i < Q; i++) {
         uint32_t L = qlens[i];
         if (L < 1 || L > s->max_bytes) return fail(ISX_EINVAL, "query %zu: length %u bytes outside 1..%u", i, L, s->max_bytes);
@@ -447,6 +448,12 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
     uint32_t tile_max = (uint32_t)std::max<size_t>(1, std::min<size_t>(kMaxTile, budget / per_query));
     tile_max = std::min<uint32_t>(tile_max, (uint32_t)Q);
 
+    uint32_t big_P = 0;
+    if (k > cap_max) {  // large k: global-memory sort scratch, one region per query of the tile
+        big_P = 1;
+        while (big_P < k) big_P <<= 1;
+        if (s->d_bigsort.ensure((size_t)tile_max * big_P * sizeof(BigRec))) return ISX_ENOMEM;
+    }
     if (s->d_queries.ensure(Q * 32) || s->d_qmap.ensure(Q * 4) || s->d_tau.ensure((size_t)tile_max * 4) ||
         s->d_hist.ensure((size_t)tile_max * R * 4) || s->d_shist.ensure((size_t)tile_max * R * 4) || s->d_cnt.ensure((size_t)tile_max * 4) ||
         s->d_ovf.ensure((size_t)tile_max * 4) || s->d_cand.ensure((size_t)tile_max * C * 8) ||
@@ -546,6 +553,8 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
         sp.out_codes = out.codes;
         sp.fallback_info = s->d_fb.as<uint32_t>();
         sp.skip_overflowed = 1;
+        sp.big_scratch = big_P ? s->d_bigsort.as<BigRec>() : nullptr;
+        sp.big_P = big_P;
         return sp;
     };
 
@@ -756,7 +765,7 @@ int isx_close(isx_store_t* s) {
     DevBuf* bufs[] = {&s->d_segs, &s->d_blocks, &s->tables.d_rank, &s->tables.d_hmax, &s->d_stage_codes, &s->d_stage_keys,
                       &s->d_stage_dest, &s->d_moves, &s->d_queries, &s->d_tau, &s->d_hist, &s->d_shist, &s->d_cnt, &s->d_ovf, &s->d_cand,
                       &s->d_qmap, &s->d_fb, &s->d_fb_cand, &s->d_out_khi, &s->d_out_klo, &s->d_out_h, &s->d_out_n,
-                      &s->d_out_cnt, &s->d_out_codes};
+                      &s->d_out_cnt, &s->d_out_codes, &s->d_bigsort};
     for (DevBuf* b : bufs) b->release();
     PinnedBuf* pbufs[] = {&s->h_queries, &s->h_qmap, &s->h_flags, &s->h_out};
     for (PinnedBuf* b : pbufs) b->release();
@@ -817,7 +826,7 @@ int isx_length_mask(isx_store_t* s, uint32_t* mask_out) {
 
 int isx_max_k(isx_store_t* s, uint32_t* k_out) {
     if (!s || !k_out) return fail(ISX_EINVAL, "NULL argument");
-    *k_out = max_sort_cap(s);
+    *k_out = kMaxK;
     return 0;
 }
 

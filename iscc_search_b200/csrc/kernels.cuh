@@ -457,7 +457,13 @@ struct SelectParams {
     uint8_t* out_codes;        // optional [Q][k][32]
     uint32_t* fallback_info;   // [T][2]: (needs fallback, count_le(d*)) for overflowed queries
     uint32_t skip_overflowed;  // 1 in the normal pass; 0 in the fallback pass (lists are complete)
+    // k beyond the shared-memory sort capacity: winners are sorted in this global scratch instead
+    // ([T][big_P] records of BigRec, big_P = power of two >= k); nullptr when k <= sort_cap
+    struct BigRec* big_scratch;
+    uint32_t big_P;
 };
+
+struct BigRec { uint64_t hi, lo; uint32_t rank, cidx; };
 
 struct SortKey { uint32_t rank; uint64_t hi, lo; };
 __device__ __forceinline__ bool key_less(const SortKey& a, const SortKey& b) {
@@ -538,7 +544,9 @@ __global__ void __launch_bounds__(kSelectThreads) k_select(const SelectParams p)
     const uint64_t* list = p.cand + (size_t)q * p.C;
     uint64_t pivot_hi = ~0ull, pivot_lo = ~0ull;  // ties with key <= pivot are winners
 
-    if (total_le > cap) {
+    const bool big = n_out > cap;                       // the winners do not fit the shared-memory sort
+    const bool use_pivot = total_le > n_out && (total_le > cap || big);  // ties at d* must be cut by key
+    if (use_pivot) {
         // ---- 2b. too many survivors for shared memory: radix-select the r-th smallest key among
         //          the ties at d*, most significant byte first (keys are unique inside a store) ----
         uint32_t need = p.k - s_count_lt;  // >= 1
@@ -595,8 +603,71 @@ __global__ void __launch_bounds__(kSelectThreads) k_select(const SelectParams p)
         __syncthreads();
     }
 
+    if (big) {
+        // ---- large k: winners -> global scratch, bitonic sort there (L2 resident), write out ----
+        BigRec* rec = p.big_scratch + (size_t)q * p.big_P;
+        for (uint32_t i = tid; i < n_list; i += kSelectThreads) {
+            uint64_t c = list[i];
+            uint32_t rk = cand_rank(c);
+            if (rk > dstar) continue;
+            const SegDesc& sd = p.segs[cand_seg(c)];
+            uint64_t hi = sd.khi[cand_row(c)];
+            uint64_t lo = (p.key_words == 2) ? sd.klo[cand_row(c)] : 0ull;
+            if (use_pivot && rk == dstar) {
+                bool le = (hi < pivot_hi) || (hi == pivot_hi && lo <= pivot_lo);
+                if (!le) continue;
+            }
+            uint32_t slot = atomicAdd(&s_fill, 1u);
+            if (slot < p.big_P) rec[slot] = BigRec{hi, lo, rk, i};
+        }
+        __syncthreads();
+        const uint32_t n_surv = min(s_fill, p.big_P);
+        uint32_t P = 1;
+        while (P < n_surv) P <<= 1;
+        for (uint32_t i = n_surv + tid; i < P; i += kSelectThreads) rec[i] = BigRec{~0ull, ~0ull, 0xffffffffu, 0};  // +inf padding
+        __syncthreads();
+        for (uint32_t size = 2; size <= P; size <<= 1) {
+            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                for (uint32_t i = tid; i < (P >> 1); i += kSelectThreads) {
+                    uint32_t lo_i = 2 * i - (i & (stride - 1));
+                    uint32_t hi_i = lo_i + stride;
+                    bool asc = ((lo_i & size) == 0);
+                    BigRec a = rec[lo_i], b = rec[hi_i];
+                    SortKey ka{a.rank, a.hi, a.lo}, kb{b.rank, b.hi, b.lo};
+                    if (key_less(kb, ka) == asc) { rec[lo_i] = b; rec[hi_i] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        const uint32_t n_write = min(n_out, n_surv);
+        for (uint32_t j = tid; j < p.k; j += kSelectThreads) {
+            size_t o = (size_t)oq * p.k + j;
+            if (j < n_write) {
+                const BigRec r = rec[j];
+                uint64_t c = list[r.cidx];
+                const SegDesc& sd = p.segs[cand_seg(c)];
+                p.out_khi[o] = r.hi;
+                p.out_klo[o] = (p.key_words == 2) ? r.lo : 0ull;
+                p.out_h[o] = (uint16_t)cand_h(c);
+                p.out_n[o] = (uint16_t)(8u * min(p.qlen_bytes, sd.len_bytes));
+            } else {
+                p.out_khi[o] = ~0ull; p.out_klo[o] = ~0ull; p.out_h[o] = 0xffffu; p.out_n[o] = 1;
+            }
+        }
+        if (p.out_codes) {
+            for (uint32_t j = tid; j < n_write * 8; j += kSelectThreads) {
+                uint32_t w = j & 7;
+                uint64_t c = list[rec[j >> 3].cidx];
+                const SegDesc& sd = p.segs[cand_seg(c)];
+                uint32_t v = (w < sd.words) ? sd.planes[(size_t)w * sd.cap + cand_row(c)] : 0u;
+                reinterpret_cast<uint32_t*>(p.out_codes)[((size_t)oq * p.k + (j >> 3)) * 8 + w] = v;
+            }
+        }
+        if (tid == 0) p.out_cnt[oq] = n_write;
+        return;
+    }
+
     // ---- 2. gather survivors (rank < d*, or rank == d* and key <= pivot) into shared memory ----
-    const bool use_pivot = (total_le > cap);
     for (uint32_t i = tid; i < n_list; i += kSelectThreads) {
         uint64_t c = list[i];
         uint32_t rk = cand_rank(c);

@@ -103,7 +103,7 @@ def test_empty_query_batch_and_empty_store(cuda):
 
 
 def test_k_at_the_supported_maximum_with_128bit_keys_and_heavy_ties(cuda):
-    # k = isx_max_k (4096 for 128-bit keys), 64-bit codes with only 65 distinct distances: the cut-off tie group is
+    # k = isx_max_k (more than the whole store), 64-bit codes with only 65 distinct distances: the cut-off tie group is
     # far larger than the shared-memory sort capacity -> radix select on the 16-byte keys
     n = 60_000
     rng = np.random.default_rng(12)
@@ -139,5 +139,36 @@ def test_byte_granular_lengths_with_threshold_and_codes_out(cuda):
         assert_same_topk(gk, gh, gn, gc, keys, rows, h, nb, cnt)
         for i in range(len(qlens)):
             assert np.array_equal(gcodes[i, : cnt[i]], codes[rows[i, : cnt[i]]])     # matched stored codes, zero padded
+    finally:
+        st.close()
+
+
+def test_k_beyond_the_shared_memory_sort_capacity(cuda):
+    # k = 10000 > 8192 (uint64 keys): winners are sorted in global scratch; mixed lengths, ties cut by key
+    st = _run(n=300_000, q=6, k=10_000, seed=909)
+    assert st["fallback_queries"] == 0
+    # 64-bit codes only: a handful of distinct distances, the tie group at the cut is far larger than any buffer slack
+    _run(n=200_000, q=4, k=9_000, seed=910, lengths=(8,), qlengths=(8,))
+
+
+def test_large_k_with_128bit_keys_and_threshold(cuda):
+    n, k = 150_000, 6_000
+    rng = np.random.default_rng(21)
+    codes = np.zeros((n, 32), dtype=np.uint8)
+    codes[:, :8] = rng.integers(0, 256, size=(n, 8), dtype=np.uint8)
+    lens = np.full(n, 8, dtype=np.uint8)
+    hi = rng.integers(0, 2**16, size=n, dtype=np.uint64)
+    lo = rng.permutation(n).astype(np.uint64)
+    keys = np.zeros((n, 16), dtype=np.uint8)
+    keys[:, :8] = hi.astype(">u8").view(np.uint8).reshape(n, 8)
+    keys[:, 8:] = lo.astype(">u8").view(np.uint8).reshape(n, 8)
+    st = Store(key_bytes=16, max_bytes=8, fixed_len=8)
+    try:
+        st.add(keys, codes, lens)
+        q, ql = codes[:3].copy(), lens[:3].copy()
+        for thr in (None, (26, 64)):
+            gk, gh, gn, gc, _ = st.search(q, ql, k, thr)
+            rows, h, nb, cnt = oracle_topk(hi, codes, lens, q, ql, k, thr, keys_lo=lo)
+            assert_same_topk(gk, gh, gn, gc, hi, rows, h, nb, cnt, keys_lo=lo)
     finally:
         st.close()
