@@ -118,11 +118,13 @@ int isx_load(isx_store_t* s, const char* path);
  * Outputs, row major q x k, first counts_out[i] entries of row i valid:
  *   keys_out (q*k*key_bytes), hamming_out, nbits_out, counts_out (q),
  *   codes_out (optional, q*k*32: the matched stored codes - replaces the per-match .get() round
- *   trips at usearch_core.py:221,243).
+ *   trips at usearch_core.py:221,243),
+ *   first_of_asset_out (optional, q*k flags, 128-bit keys: 1 where a record is the best one of its asset
+ *   = high 8 key bytes within its query - the grouping loop of usearch_core.py:187-196 done on the device).
  */
 int isx_search(isx_store_t* s, const uint8_t* queries, const uint8_t* qlens, size_t q, uint32_t k,
                uint32_t thr_num, uint32_t thr_den, void* keys_out, uint16_t* hamming_out, uint16_t* nbits_out,
-               uint32_t* counts_out, uint8_t* codes_out);
+               uint32_t* counts_out, uint8_t* codes_out, uint8_t* first_of_asset_out);
 
 /*
  * Same search, results left in DEVICE memory as q x k records (for the multi-GPU merge):

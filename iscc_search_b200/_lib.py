@@ -100,7 +100,7 @@ def lib():
     L.isx_length_mask.argtypes = [vp, P(u32)]
     L.isx_save.argtypes = [vp, cp]
     L.isx_load.argtypes = [vp, cp]
-    L.isx_search.argtypes = [vp, vp, vp, sz, u32, u32, u32, vp, vp, vp, vp, vp]
+    L.isx_search.argtypes = [vp, vp, vp, sz, u32, u32, u32, vp, vp, vp, vp, vp, vp]
     L.isx_search_device.argtypes = [vp, vp, ci, vp, sz, u32, u32, u32, vp, vp, vp, vp, vp, ci]
     L.isx_merge_device.argtypes = [vp, u32, sz, u32, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci]
     L.isx_max_k.argtypes = [vp, P(u32)]
@@ -221,9 +221,12 @@ class Store:
         check(lib().isx_load(self.handle, os.fsencode(str(path))))
 
     # -- search
-    def search(self, queries, qlens, k, thr=None, with_codes=False):
-        # type: (np.ndarray, np.ndarray, int, tuple[int,int]|None, bool) -> tuple
-        """-> (keys, hamming uint16[Q,k], nbits uint16[Q,k], counts uint32[Q], codes|None)."""
+    def search(self, queries, qlens, k, thr=None, with_codes=False, first_of_asset=None):
+        # type: (np.ndarray, np.ndarray, int, tuple[int,int]|None, bool, np.ndarray|None) -> tuple
+        """
+        -> (keys, hamming uint16[Q,k], nbits uint16[Q,k], counts uint32[Q], codes|None).
+        `first_of_asset`: optional uint8[Q,k] output, 1 where a record is the best of its asset within its query.
+        """
         q = len(qlens)
         if k < 1:
             raise ValueError("`count` must be >= 1")
@@ -233,7 +236,8 @@ class Store:
         counts = np.zeros(q, dtype=np.uint32)
         codes = np.zeros((q, k, 32), dtype=np.uint8) if with_codes else None
         tn, td = (0, 0) if thr is None else thr
-        check(lib().isx_search(self.handle, ptr(queries), ptr(qlens), q, k, tn, td, ptr(keys), ptr(h), ptr(nb), ptr(counts), ptr(codes)))
+        check(lib().isx_search(self.handle, ptr(queries), ptr(qlens), q, k, tn, td, ptr(keys), ptr(h), ptr(nb), ptr(counts), ptr(codes),
+                               ptr(first_of_asset)))
         return keys, h, nb, counts, codes
 
     def match_all(self, query, thr=(0, 1), max_out=4096):

@@ -435,7 +435,8 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
         tau_init = r;
     }
 
-    // bootstrap plan (block units): round 0 accepts everything over r0 blocks, then ranges grow 8x
+    // candidate buffer per query: a few k for the logarithmic tail of the running threshold plus slack for the
+    // rows accepted before the first feedback (first wave of the bulk launch); overflow is handled exactly anyway
     const uint32_t r0 = std::max<uint32_t>(1, (2 * k + kBlockRows - 1) / kBlockRows);
     uint64_t C64 = (uint64_t)r0 * kBlockRows + 40ull * k + 2048;
     C64 = std::max<uint64_t>(C64, 32768);  // slack for the delayed threshold feedback of the first wave
@@ -1004,7 +1005,7 @@ int isx_get(isx_store_t* s, const void* keys, size_t n, uint8_t* codes_out, uint
 
 int isx_search(isx_store_t* s, const uint8_t* queries, const uint8_t* qlens, size_t q, uint32_t k, uint32_t thr_num,
                uint32_t thr_den, void* keys_out, uint16_t* hamming_out, uint16_t* nbits_out, uint32_t* counts_out,
-               uint8_t* codes_out) {
+               uint8_t* codes_out, uint8_t* first_of_asset_out) {
     if (!s) return fail(ISX_EINVAL, "store is NULL");
     if (k < 1) return fail(ISX_EINVAL, "`count` must be >= 1");
     if (q == 0) return 0;
@@ -1020,6 +1021,19 @@ int isx_search(isx_store_t* s, const uint8_t* queries, const uint8_t* qlens, siz
     SearchOut out{s->d_out_khi.as<uint64_t>(), s->d_out_klo.as<uint64_t>(), s->d_out_h.as<uint16_t>(), s->d_out_n.as<uint16_t>(),
                   s->d_out_cnt.as<uint32_t>(), codes_out ? s->d_out_codes.as<uint8_t>() : nullptr};
     if ((rc = search_core(s, queries, false, qlens, q, k, thr_num, thr_den, out))) return rc;
+    if (first_of_asset_out) {
+        // device-side grouping of simprint matches: flag the best record of every asset per query
+        uint32_t H = 2;
+        while (H < 2 * k) H <<= 1;
+        const size_t smem = (size_t)H * 12 + 16;
+        if (smem + 1024 > (size_t)s->max_smem_optin) return fail(ISX_ELIMIT, "first_of_asset_out supports count <= %u", (uint32_t)(s->max_smem_optin / 24 / 2));
+        if (s->d_stage_codes.ensure(qk)) return ISX_ENOMEM;
+        CU(cudaFuncSetAttribute(k_first_per_asset, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem_optin - 64));
+        k_first_per_asset<<<(unsigned)q, 512, smem, s->stream>>>(out.khi, out.cnt, k, H, s->d_stage_codes.as<uint8_t>());
+        CU(cudaGetLastError());
+        s->stats.kernel_launches++;
+        CU(cudaMemcpyAsync(first_of_asset_out, s->d_stage_codes.p, qk, cudaMemcpyDeviceToHost, s->stream));
+    }
     // results -> pinned staging -> caller
     size_t bytes = qk * (8 + 8 + 2 + 2) + q * 4;
     if (s->h_out.ensure(bytes)) return ISX_ENOMEM;

@@ -843,6 +843,45 @@ __global__ void k_move_rows(const SegDesc* segs, const uint4* moves, size_t n) {
     }
 }
 
+// Simprint grouping on the device: per query, flag the FIRST (= best, lists are sorted) record of
+// every asset, asset = high 8 bytes of the 128-bit composite key (usearch_core.py:187-196 keeps exactly that record
+// per (asset, query)). One CTA per query, open-addressing table in shared memory: slot -> (asset, smallest index).
+__global__ void k_first_per_asset(const uint64_t* khi, const uint32_t* cnt, uint32_t k, uint32_t H, uint8_t* first) {
+    extern __shared__ uint4 smem_raw[];
+    unsigned long long* s_asset = reinterpret_cast<unsigned long long*>(smem_raw);  // [H], ~0 = empty slot
+    uint32_t* s_min = reinterpret_cast<uint32_t*>(s_asset + H);                      // [H]
+    __shared__ uint32_t s_all_ones_min;  // the one asset id that collides with the empty marker is tracked apart
+    const uint32_t q = blockIdx.x, n = min(cnt[q], k), mask = H - 1;
+    const uint64_t* kq = khi + (size_t)q * k;
+    for (uint32_t i = threadIdx.x; i < H; i += blockDim.x) { s_asset[i] = ~0ull; s_min[i] = 0xffffffffu; }
+    if (threadIdx.x == 0) s_all_ones_min = 0xffffffffu;
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
+        const unsigned long long a = kq[j];
+        if (a == ~0ull) { atomicMin(&s_all_ones_min, j); continue; }
+        uint32_t h = (uint32_t)((a * 0x9E3779B97F4A7C15ull) >> 40) & mask;
+        for (;;) {
+            const unsigned long long prev = atomicCAS(&s_asset[h], ~0ull, a);
+            if (prev == ~0ull || prev == a) { atomicMin(&s_min[h], j); break; }
+            h = (h + 1) & mask;
+        }
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) {
+        uint8_t f = 0;
+        if (j < n) {
+            const unsigned long long a = kq[j];
+            if (a == ~0ull) f = (s_all_ones_min == j);
+            else {
+                uint32_t h = (uint32_t)((a * 0x9E3779B97F4A7C15ull) >> 40) & mask;
+                while (s_asset[h] != a) h = (h + 1) & mask;
+                f = (s_min[h] == j);
+            }
+        }
+        first[(size_t)q * k + j] = f;
+    }
+}
+
 // queries (device, caller order) -> group order: dst[i] = src[order[i]], 32 bytes per query, bytes beyond the
 // query's length zeroed (8 threads per query, one word each)
 __global__ void k_gather_queries(const uint32_t* src, const uint32_t* order, const uint8_t* qlens_sorted, uint32_t* dst, uint32_t Q) {

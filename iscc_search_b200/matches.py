@@ -26,6 +26,7 @@ class Matches:
     hamming: np.ndarray = None  # uint16[c]
     nbits: np.ndarray = None  # uint16[c]
     vectors: np.ndarray = None  # uint8[c,32] matched stored codes (optional)
+    first: np.ndarray = None  # uint8[c] 1 where the record is the best of its asset (optional, 128-bit keys)
     visited_members: int = 0
     computed_distances: int = 0
 
@@ -58,6 +59,7 @@ class BatchMatches:
     hamming: np.ndarray = None
     nbits: np.ndarray = None
     vectors: np.ndarray = None
+    first: np.ndarray = None
     visited_members: int = 0
     computed_distances: int = 0
 
@@ -74,6 +76,7 @@ class BatchMatches:
             hamming=None if self.hamming is None else self.hamming[i, :c],
             nbits=None if self.nbits is None else self.nbits[i, :c],
             vectors=None if self.vectors is None else self.vectors[i, :c],
+            first=None if self.first is None else self.first[i, :c],
             visited_members=self.visited_members // max(len(self), 1),
             computed_distances=self.computed_distances // max(len(self), 1),
         )

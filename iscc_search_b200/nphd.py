@@ -304,12 +304,14 @@ class ShardedIndex128(_IndexBase):
         out = [codes[i, : lens[i]].copy() if lens[i] else None for i in range(len(k))]
         return out[0] if scalar else out
 
-    def search(self, vectors, count=10, exact=True, threshold_bits=None, with_vectors=False, **_ignored):
+    def search(self, vectors, count=10, exact=True, threshold_bits=None, with_vectors=False, with_first=False, **_ignored):
         """
         Exact top-`count` by Hamming distance; distances are raw bit counts as float32.
         A single 1-D query returns a bare `Matches` (usearch_core.py:167-169), a batch `BatchMatches`.
         `threshold_bits` (extension): keep only rows with h <= threshold_bits (h == 0: equality join).
         `with_vectors` (extension): also return the matched stored codes (replaces `.get` per match).
+        `with_first` (extension): also return per-record flags marking the best record of every asset
+        (asset = first 8 key bytes) within its query - the grouping of usearch_core.py:187-196, done on the device.
         """
         if count < 1:
             raise ValueError("`count` must be >= 1")
@@ -317,7 +319,8 @@ class ShardedIndex128(_IndexBase):
         single = len(qlens) == 1  # bare Matches for one query (usearch_core.py:167-169), also for a (1, n) array
         kk = max(1, min(int(count), max(self._store.size(), 1)))
         thr = None if threshold_bits is None else (int(threshold_bits), self.ndim)
-        keys, h, nb, counts, codes = self._store.search(queries, qlens, kk, thr, with_vectors)
+        first = np.zeros((len(qlens), kk), dtype=np.uint8) if with_first else None
+        keys, h, nb, counts, codes = self._store.search(queries, qlens, kk, thr, with_vectors, first)
         dist = h.astype(np.float32)
         nbytes = self.ndim // 8
         vec = codes[:, :, :nbytes] if codes is not None else None
@@ -325,6 +328,7 @@ class ShardedIndex128(_IndexBase):
         if single:
             c = int(counts[0])
             return Matches(keys=keys[0, :c], distances=dist[0, :c], hamming=h[0, :c], nbits=nb[0, :c],
-                           vectors=None if vec is None else vec[0, :c], visited_members=n_rows, computed_distances=n_rows)
-        return BatchMatches(keys=keys, distances=dist, counts=counts.astype(np.int64), hamming=h, nbits=nb, vectors=vec,
+                           vectors=None if vec is None else vec[0, :c], first=None if first is None else first[0, :c],
+                           visited_members=n_rows, computed_distances=n_rows)
+        return BatchMatches(keys=keys, distances=dist, counts=counts.astype(np.int64), hamming=h, nbits=nb, vectors=vec, first=first,
                             visited_members=n_rows * len(qlens), computed_distances=n_rows * len(qlens))

@@ -85,3 +85,31 @@ def test_reference_behaviours_restated(cuda):
     assert k1 not in idx and idx.size == 2
     assert all(r.iscc_id_body != a1 or r.matches == 1 for r in idx.search_raw([sp1, sp2], limit=10, threshold=0.9, total_assets=2))
     idx.close()
+
+
+def test_first_of_asset_flags_equal_host_grouping(cuda):
+    # device-side grouping (isx_search first_of_asset_out) against the numpy first-occurrence of the asset id
+    from iscc_search_b200 import ShardedIndex128
+
+    rng = np.random.default_rng(4)
+    n, nq, count = 40_000, 9, 3000
+    assets = rng.integers(0, 500, size=n, dtype=np.uint64)
+    assets[:50] = np.uint64(2**64 - 1)                       # the asset id that equals the table's empty marker
+    keys = np.zeros((n, 16), dtype=np.uint8)
+    keys[:, :8] = assets.astype(">u8").view(np.uint8).reshape(n, 8)
+    keys[:, 8:] = np.arange(n, dtype=np.uint64).astype(">u8").view(np.uint8).reshape(n, 8)
+    vecs = rng.integers(0, 256, size=(n, 8), dtype=np.uint8)
+    idx = ShardedIndex128(ndim=64)
+    idx.add(keys, vecs)
+    res = idx.search(vecs[:nq], count=count, with_first=True)
+    assert res.first.shape == (nq, count)
+    for i in range(nq):
+        c = int(res.counts[i])
+        a = np.ascontiguousarray(res.keys[i, :c, :8]).view(">u8").ravel()
+        _, first_idx = np.unique(a, return_index=True)
+        expect = np.zeros(c, dtype=np.uint8)
+        expect[first_idx] = 1
+        assert np.array_equal(res.first[i, :c], expect)
+    single = idx.search(vecs[0], count=10, with_first=True)
+    assert single.first.shape == (10,) and single.first[0] == 1
+    idx.close()
