@@ -361,10 +361,15 @@ static int scan_range(isx_store* s, ScanParams& p, uint32_t b0, uint32_t b1, uin
                 side_used++;
             }
             n_launch++;
-            uint64_t rows = 0;  // live rows in the range (last block of a segment may be partial)
-            for (uint32_t b = lo; b < hi; b++) {
-                const SegDesc& d = s->segs[s->h_blocks[b].x].desc;
-                rows += std::min<uint32_t>(kBlockRows, d.n - s->h_blocks[b].y);
+            uint64_t rows = 0;  // live rows in the range: whole buckets from the bucket counters, partial ones block by block
+            for (uint32_t Lb = L; Lb <= Lhi; Lb++) {
+                const uint32_t blo = std::max(lo, s->bucket_block_lo[Lb]), bhi = std::min(hi, s->bucket_block_lo[Lb + 1]);
+                if (blo >= bhi) continue;
+                if (blo == s->bucket_block_lo[Lb] && bhi == s->bucket_block_lo[Lb + 1]) { rows += s->bucket_rows[Lb]; continue; }
+                for (uint32_t b = blo; b < bhi; b++) {  // last block of a segment may be partial
+                    const SegDesc& d = s->segs[s->h_blocks[b].x].desc;
+                    rows += std::min<uint32_t>(kBlockRows, d.n - s->h_blocks[b].y);
+                }
             }
             s->stats.pairs += rows * p.T;
             s->stats.algo_bytes += rows * m;

@@ -441,6 +441,8 @@ __global__ void k_init_queries(uint32_t* tau, uint32_t* hist, uint32_t* sample_h
 
 // ---------------------------------------------------------------------------------------------
 // Final exact selection: one CTA per query.
+struct BigRec { uint64_t hi, lo; uint32_t rank, cidx; };  // sort record of the large-k path (global scratch)
+
 struct SelectParams {
     const SegDesc* segs;
     const uint32_t* hist;      // [T][R]
@@ -459,11 +461,9 @@ struct SelectParams {
     uint32_t skip_overflowed;  // 1 in the normal pass; 0 in the fallback pass (lists are complete)
     // k beyond the shared-memory sort capacity: winners are sorted in this global scratch instead
     // ([T][big_P] records of BigRec, big_P = power of two >= k); nullptr when k <= sort_cap
-    struct BigRec* big_scratch;
+    BigRec* big_scratch;
     uint32_t big_P;
 };
-
-struct BigRec { uint64_t hi, lo; uint32_t rank, cidx; };
 
 struct SortKey { uint32_t rank; uint64_t hi, lo; };
 __device__ __forceinline__ bool key_less(const SortKey& a, const SortKey& b) {
