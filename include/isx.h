@@ -178,6 +178,15 @@ int isx_share_init(isx_store_t* s, uint32_t world, uint32_t rank, uint32_t max_q
 int isx_share_attach(isx_store_t* s, uint32_t peer_rank, const void* handle);
 int isx_share_reset(isx_store_t* s);
 
+/*
+ * Host-only self tests (no CUDA device needed; used by the CPU test-suite):
+ *   isx_selftest_rank_table  the dense rank of every h/(8m) for the compared-length classes in class_mask
+ *                            (bit m-1), rank_out[33][257] (0xFFFF = unused), optional hmax_out[33][hmax_stride]
+ *   isx_selftest_keymap      randomized insert/update/erase/find of the key -> row map against a reference
+ */
+int isx_selftest_rank_table(uint32_t class_mask, uint16_t* rank_out, uint16_t* hmax_out, uint32_t hmax_stride, uint32_t* R_out);
+int isx_selftest_keymap(uint64_t n_ops, uint64_t seed, uint32_t key_space);
+
 /* largest k isx_search accepts for this store (shared-memory bound of the final selection) */
 int isx_max_k(isx_store_t* s, uint32_t* k_out);
 

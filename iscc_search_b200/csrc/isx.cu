@@ -244,9 +244,7 @@ static int upload_blocks(isx_store* s) {
 // ---- rank tables -------------------------------------------------------------------------------
 // Dense rank of every rational h/(8m) over the compared-length classes in `mask`; exact integer
 // order via cross multiplication. hmax[m][r] = largest h with rank(m,h) <= r.
-static int build_tables(isx_store* s, uint32_t mask) {
-    RankTables& t = s->tables;
-    if (t.class_mask == mask && t.R) return 0;
+static int compute_tables(uint32_t mask, RankTables& t) {
     struct F { uint32_t h, n, m; };
     std::vector<F> fr;
     for (uint32_t m = 1; m <= kMaxBytes; m++)
@@ -277,6 +275,17 @@ static int build_tables(isx_store* s, uint32_t mask) {
             t.hmax[(size_t)m * t.R + rr] = (uint16_t)h;
         }
     }
+    t.class_mask = mask;
+    return 0;
+}
+
+static int build_tables(isx_store* s, uint32_t mask) {
+    RankTables& t = s->tables;
+    if (t.class_mask == mask && t.R) return 0;
+    t.class_mask = 0;
+    int rc = compute_tables(mask, t);
+    if (rc) return rc;
+    t.class_mask = 0;  // set again only after the upload succeeded
     if (t.d_rank.ensure(t.rank.size() * 2) || t.d_hmax.ensure(t.hmax.size() * 2)) return ISX_ECUDA;
     CU(cudaMemcpyAsync(t.d_rank.p, t.rank.data(), t.rank.size() * 2, cudaMemcpyHostToDevice, s->stream));
     CU(cudaMemcpyAsync(t.d_hmax.p, t.hmax.data(), t.hmax.size() * 2, cudaMemcpyHostToDevice, s->stream));
@@ -1221,6 +1230,63 @@ int isx_share_reset(isx_store_t* s) {
     for (uint32_t r = 0; r < s->share_world; r++)
         if (!s->share_ptrs[r]) return fail(ISX_EINVAL, "peer %u is not attached", r);
     CU(cudaMemsetAsync(s->share_local, 0, s->share_bytes, s->stream));
+    return 0;
+}
+
+// ---- host-only self tests (no device needed): used by the CPU test-suite ------------------------------------
+int isx_selftest_rank_table(uint32_t class_mask, uint16_t* rank_out, uint16_t* hmax_out, uint32_t hmax_stride, uint32_t* R_out) {
+    if (!rank_out || !R_out) return fail(ISX_EINVAL, "NULL argument");
+    RankTables t;
+    int rc = compute_tables(class_mask, t);
+    if (rc) return rc;
+    memcpy(rank_out, t.rank.data(), t.rank.size() * 2);
+    *R_out = t.R;
+    if (hmax_out) {
+        if (hmax_stride < t.R) return fail(ISX_EINVAL, "hmax_stride %u < R %u", hmax_stride, t.R);
+        for (uint32_t m = 0; m <= kMaxBytes; m++) memcpy(hmax_out + (size_t)m * hmax_stride, t.hmax.data() + (size_t)m * t.R, t.R * 2);
+    }
+    return 0;
+}
+
+int isx_selftest_keymap(uint64_t n_ops, uint64_t seed, uint32_t key_space) {
+    // random insert / update / erase / find against a std::vector reference over a small key space (many collisions
+    // of home slots and long probe chains: exercises the backward-shift deletion)
+    KeyMap map;
+    std::vector<uint64_t> ref(key_space, ~0ull);
+    uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1;
+    auto next = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    size_t live = 0;
+    for (uint64_t i = 0; i < n_ops; i++) {
+        uint64_t r = next();
+        uint32_t kidx = (uint32_t)(r % key_space);
+        Key128 key{mix64(kidx) | 1, mix64(kidx * 31ull + 5)};  // one fixed 128-bit key per kidx
+        uint32_t op = (uint32_t)((r >> 32) % 4);
+        uint64_t loc;
+        bool present = ref[kidx] != ~0ull;
+        if (op == 0) {
+            bool ok = map.insert(key, r >> 8 & 0xffffffffffull);
+            if (ok == present) return fail(ISX_EINVAL, "keymap: insert result mismatch at op %llu", (unsigned long long)i);
+            if (ok) { ref[kidx] = r >> 8 & 0xffffffffffull; live++; }
+        } else if (op == 1) {
+            bool ok = map.erase(key);
+            if (ok != present) return fail(ISX_EINVAL, "keymap: erase result mismatch at op %llu", (unsigned long long)i);
+            if (ok) { ref[kidx] = ~0ull; live--; }
+        } else if (op == 2) {
+            bool ok = map.update(key, i);
+            if (ok != present) return fail(ISX_EINVAL, "keymap: update result mismatch at op %llu", (unsigned long long)i);
+            if (ok) ref[kidx] = i;
+        } else {
+            bool ok = map.find(key, &loc);
+            if (ok != present || (ok && loc != ref[kidx])) return fail(ISX_EINVAL, "keymap: find mismatch at op %llu", (unsigned long long)i);
+        }
+        if (map.size() != live) return fail(ISX_EINVAL, "keymap: size mismatch at op %llu", (unsigned long long)i);
+    }
+    for (uint32_t kidx = 0; kidx < key_space; kidx++) {  // final sweep: every key answers like the reference
+        Key128 key{mix64(kidx) | 1, mix64(kidx * 31ull + 5)};
+        uint64_t loc;
+        bool ok = map.find(key, &loc);
+        if (ok != (ref[kidx] != ~0ull) || (ok && loc != ref[kidx])) return fail(ISX_EINVAL, "keymap: final sweep mismatch at key %u", kidx);
+    }
     return 0;
 }
 

@@ -1,0 +1,56 @@
+"""CPU tests (no GPU) of the library's host logic through its self-test entry points: rank tables and the key map."""
+
+import ctypes
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+from iscc_search_b200 import _lib
+
+
+def _tables(mask, stride=8192):
+    rank = np.zeros((33, 257), dtype=np.uint16)
+    hmax = np.zeros((33, stride), dtype=np.uint16)
+    R = ctypes.c_uint32()
+    _lib.check(_lib.lib().isx_selftest_rank_table(mask, _lib.ptr(rank), _lib.ptr(hmax), stride, ctypes.byref(R)))
+    return rank, hmax, int(R.value)
+
+
+@pytest.mark.parametrize("lengths", [(8, 16, 24, 32), (8,), (4, 5, 12, 13, 20, 27, 32), tuple(range(1, 33))])
+def test_rank_table_is_the_dense_rank_of_the_exact_rational(lengths):
+    mask = 0
+    for m in lengths:
+        mask |= 1 << (m - 1)
+    rank, hmax, R = _tables(mask)
+    fracs = sorted({Fraction(h, 8 * m) for m in lengths for h in range(8 * m + 1)})
+    assert R == len(fracs)
+    if lengths == (8, 16, 24, 32):
+        assert R == 385  # 257 + 193 - 65 distinct values
+    index = {f: i for i, f in enumerate(fracs)}
+    for m in range(1, 33):
+        if m in lengths:
+            got = rank[m, : 8 * m + 1].astype(int)
+            assert [int(x) for x in got] == [index[Fraction(h, 8 * m)] for h in range(8 * m + 1)]
+            assert (rank[m, 8 * m + 1:] == 0xFFFF).all()
+            # hmax[m][r] = largest h whose rank is <= r: monotone, consistent with rank, and 0/1 -> h=0 only
+            for r in (0, 1, R // 3, R - 1):
+                h = int(hmax[m, r])
+                assert rank[m, h] <= r and (h == 8 * m or rank[m, h + 1] > r)
+            assert (np.diff(hmax[m, :R].astype(int)) >= 0).all() and hmax[m, 0] == 0 and hmax[m, R - 1] == 8 * m
+        else:
+            assert (rank[m] == 0xFFFF).all()
+
+
+def test_equal_fractions_of_different_lengths_share_a_rank():
+    rank, _, _ = _tables((1 << 7) | (1 << 15) | (1 << 31))
+    assert rank[8, 16] == rank[16, 32] == rank[32, 64]      # 16/64 = 32/128 = 64/256
+    assert rank[8, 1] > rank[32, 3] and rank[8, 1] < rank[32, 5]  # 1/64 = 4/256 sits between 3/256 and 5/256
+    assert rank[8, 1] == rank[32, 4]
+
+
+def test_keymap_randomized_against_reference():
+    L = _lib.lib()
+    for seed, ops, space in ((1, 200_000, 64), (2, 300_000, 1500), (3, 400_000, 50_000)):
+        rc = L.isx_selftest_keymap(ops, seed, space)
+        assert rc == 0, L.isx_last_error()
