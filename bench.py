@@ -44,7 +44,7 @@ HBM_FALLBACK_GBS = 6650.0    # /opt/skills/guides/B200_PROFILING.md fallback whe
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=100_000_000)
@@ -65,51 +65,111 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md recipe)."""
+    """
+    SM clock / throttle-reason samples taken DURING the timed region (B200_PROFILING.md's clocks line): an NVML
+    polling thread in this process (2 ms period; `nvidia-smi -lms` cannot sample a sub-second region), falling back
+    to an `nvidia-smi -lms 100` child when NVML is unusable. Only samples between mark_begin() and mark_end() count.
+    """
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+    def __init__(self, gpu_index, uuid=None):
+        self.gpu_index, self.uuid = gpu_index, uuid
+        self.proc, self.thread, self.stop_flag = None, None, threading.Event()
+        self.samples = []   # (t, sm_mhz, reasons bitmask or set)
+        self.smax = None
+        self.t0 = self.t1 = None
+        self.how = None
+
+    def _nvml_handle(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        if self.uuid:
+            try:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(self.uuid)
+            except Exception:
+                pass
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = self.gpu_index
+        if vis and all(x.strip().isdigit() for x in vis.split(",")):
+            idx = int(vis.split(",")[self.gpu_index])
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
 
     def start(self):
         try:
+            nv, h = self._nvml_handle()
+            self.smax = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+
+            def poll():
+                while not self.stop_flag.is_set():
+                    try:
+                        mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                        mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        self.samples.append((time.perf_counter(), mhz, {n for n, bit in names.items() if mask & bit}))
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+
+            self.how = "nvml"
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            pass
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.how = "nvidia-smi"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
     def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.strip().split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
+                mhz, smax = float(f[1]), float(f[2])
             except ValueError:
                 continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            self.smax = max(self.smax or 0.0, smax)
+            self.samples.append((time.perf_counter(), mhz, {n for n, v in zip(names, f[5:9]) if v.lower().startswith("active")}))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if self.thread:
+            self.thread.join(timeout=2)
+        if self.how is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source (NVML and nvidia-smi unavailable)"], "samples": 0}
+        inside = [x for x in self.samples if self.t0 is not None and self.t1 is not None and self.t0 <= x[0] <= self.t1]
+        window = "timed region"
+        if not inside:   # region shorter than the sampling period of the fallback source: use everything sampled under load
+            inside, window = self.samples, "warm-up + timed region"
+        reasons = set()
+        for _t, _mhz, r in inside:
+            reasons |= r
+        return {"sm_mhz": float(np.median([x[1] for x in inside])) if inside else None, "sm_max_mhz": self.smax,
+                "reasons": sorted(reasons), "samples": len(inside), "source": self.how, "window": window}
 
 
 def gen_shard(synth, start, n, seed, sink, chunk=2_000_000):
@@ -254,13 +314,18 @@ def main():
         return res, store.stats()
 
     # ---- warm-up, then K timed steps (device-resident inputs). The store (2 GB) is far larger than L2. ----
-    sampler = ClockSampler(local_rank)  # started before the warm-up: nvidia-smi needs ~0.5 s before its first sample
+    try:
+        gpu_uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local_rank, gpu_uuid)  # started before the warm-up so that the first sample is there in time
     sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches, scan_ms, algo_popc, issued_popc, pairs, cands, fallbacks = 0, 0.0, 0, 0, 0, 0, 0
+    sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
         st = step_device()
@@ -273,6 +338,7 @@ def main():
         fallbacks += st["fallback_queries"]
     e1.record()
     barrier()
+    sampler.mark_end()
     ms_total = e0.elapsed_time(e1)
     t = torch.tensor([ms_total], device=dev)
     if world > 1:

@@ -383,7 +383,7 @@ static int scan_range(isx_store* s, ScanParams& p, uint32_t b0, uint32_t b1, uin
             s->stats.pairs += rows * p.T;
             s->stats.algo_bytes += rows * m;
             s->stats.algo_popc += rows * p.T * ((m + 3) / 4);
-            static const uint32_t kCsaPopc[9] = {0, 1, 1, 2, 2, 3, 3, 4, 5};  // steady state: lower-bound filter (2,4,5,6 words) else carry-save
+            static const uint32_t kCsaPopc[9] = {0, 1, 1, 2, 2, 3, 2, 3, 3};  // steady state: OR-fold lower-bound filter (3-word folds for 6..8 words, 2-word folds for 2, 4, 5) else carry-save
             s->stats.issued_popc += rows * p.T * kCsaPopc[(m + 3) / 4];
         }
         if (Lhi == kMaxBytes) break;

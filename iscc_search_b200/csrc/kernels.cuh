@@ -183,22 +183,41 @@ __device__ __forceinline__ uint32_t pair_distance(const uint32_t (&x)[WE]) {
 
 __device__ __forceinline__ uint32_t comp(const uint4& v, int r) { return r == 0 ? v.x : r == 1 ? v.y : r == 2 ? v.z : v.w; }
 
-// Cheap LOWER bound of the distance: popc(x0 | x1) <= popc(x0) + popc(x1), one POPC per word pair.
-// A row whose bound already exceeds the query's current Hamming bound cannot be a candidate, so once the
-// running threshold is tight the exact distance is only evaluated for the rare warp slots where some
-// lane's bound passes. Exact by construction (the bound never over-estimates). Pays for 2, 4, 5, 6 words.
+// Cheap LOWER bounds of the distance: popc(x0 | x1 [| x2]) <= popc(x0) + popc(x1) [+ popc(x2)], one POPC per
+// group of F words (the OR rides in the XOR's LOP3). A row whose bound already exceeds the query's current
+// Hamming bound cannot be a candidate, so once the running threshold is tight the exact distance is only
+// evaluated for the rare warp slots where some lane's bound passes. Exact by construction (the bound never
+// over-estimates). Two tiers: folds of 3 words (6, 7, 8 words: 2, 3, 3 POPC) when the bound is very tight,
+// folds of 2 words (2, 4, 5, 6, 8 words: 1, 2, 3, 3, 4 POPC) otherwise.
+// Cutoffs = largest Hamming bound for which the filter is expected to reject almost every random row:
+// mean - 2.75 sigma of the bound under uniformly random codes (an OR of f words ~ Bin(32, 1 - 2^-f)).
 template <int WE>
 struct LowerBound {
-    static constexpr bool kUseful = (WE == 2 || WE == 4 || WE == 5 || WE == 6);
-    // largest Hamming bound for which the filter is expected to reject almost every random row:
-    // mean - 2.75 sigma of the bound under uniformly random codes (pairs ~ Bin(32, 3/4), singles ~ Bin(32, 1/2))
-    static constexpr uint32_t kCutoff = WE == 2 ? 17u : WE == 4 ? 38u : WE == 5 ? 50u : WE == 6 ? 60u : 0u;
-    __device__ __forceinline__ static uint32_t eval(const uint32_t (&x)[WE]) {
-        if constexpr (WE == 2) return __popc(x[0] | x[1]);
-        else if constexpr (WE == 4) return __popc(x[0] | x[1]) + __popc(x[2] | x[3]);
-        else if constexpr (WE == 5) return __popc(x[0] | x[1]) + __popc(x[2] | x[3]) + __popc(x[4]);
-        else if constexpr (WE == 6) return __popc(x[0] | x[1]) + __popc(x[2] | x[3]) + __popc(x[4] | x[5]);
-        else return 0;
+    static constexpr uint32_t kCutoff3 = WE == 6 ? 48u : WE == 7 ? 61u : WE == 8 ? 70u : 0u;
+    static constexpr uint32_t kCutoff2 = WE == 2 ? 17u : WE == 4 ? 38u : WE == 5 ? 50u : WE == 6 ? 60u : WE == 8 ? 82u : 0u;
+    // bound of row r of a 4-row group straight from the planes
+    template <int F>
+    __device__ __forceinline__ static uint32_t eval(const uint4 (&a)[WE], const uint32_t (&qv)[WE], int r, uint32_t mask_last) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int w = 0; w < WE; w += F) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int j = 0; j < F; j++) {
+                if (w + j < WE) {
+                    uint32_t x = comp(a[w + j], r) ^ qv[w + j];
+                    if (w + j == WE - 1) x &= mask_last;
+                    t |= x;
+                }
+            }
+            acc += __popc(t);
+        }
+        return acc;
+    }
+    template <int F>
+    __device__ __forceinline__ static uint32_t min4(const uint4 (&a)[WE], const uint32_t (&qv)[WE], uint32_t mask_last) {
+        return min(min(eval<F>(a, qv, 0, mask_last), eval<F>(a, qv, 1, mask_last)),
+                   min(eval<F>(a, qv, 2, mask_last), eval<F>(a, qv, 3, mask_last)));
     }
 };
 
@@ -291,24 +310,14 @@ __global__ void __launch_bounds__(kThreads, MINB) k_scan(const __grid_constant__
                     }
                 }
                 const uint32_t hmax = hm[q];
-                const bool filtered = LowerBound<WE>::kUseful && hmax <= LowerBound<WE>::kCutoff;  // uniform per query
+                // filter tier, uniform per query: 3 = folds of three words, 2 = folds of two, 0 = none
+                const int tier = hmax <= LowerBound<WE>::kCutoff3 ? 3 : hmax <= LowerBound<WE>::kCutoff2 ? 2 : 0;
 #pragma unroll
                 for (int g = 0; g < G; g++) {
-                    if (filtered) {
-                        // bound straight from the planes: (a0^q0) | ((a1^q1)&mask) is two LOP3 per word pair
-                        uint32_t lb[4];
-#pragma unroll
-                        for (int r = 0; r < 4; r++) {
-                            uint32_t acc = 0;
-#pragma unroll
-                            for (int w = 0; w + 1 < WE; w += 2) {
-                                const uint32_t mk = (w + 1 == WE - 1) ? mask_last : 0xffffffffu;
-                                acc += __popc((comp(a[g][w], r) ^ qv[w]) | ((comp(a[g][w + 1], r) ^ qv[w + 1]) & mk));
-                            }
-                            if (WE & 1) acc += __popc((comp(a[g][WE - 1], r) ^ qv[WE - 1]) & mask_last);
-                            lb[r] = acc;
-                        }
-                        const uint32_t lbmin = min(min(lb[0], lb[1]), min(lb[2], lb[3]));
+                    if (tier) {
+                        const uint32_t lbmin = (LowerBound<WE>::kCutoff3 && tier == 3)
+                                                   ? LowerBound<WE>::template min4<3>(a[g], qv, mask_last)
+                                                   : LowerBound<WE>::template min4<2>(a[g], qv, mask_last);
                         if (!__any_sync(0xffffffffu, lbmin <= hmax)) continue;  // no lane can have a candidate in this slot
                     }
                     uint32_t d[4];
