@@ -416,7 +416,7 @@ def main():
                           "peak_kind": f"measured {POPC_PER_CLK_PER_SM}/clk/SM x 148 SM x {sm_max_mhz:.0f} MHz",
                           "regime": f"{Q} queries per step (timed region)", "scan_ms_per_step": scan_ms / args.steps,
                           "note": "achieved counts ALGORITHMIC popcounts (ceil(min(Lq,Lb)/4) per pair); the kernel issues fewer "
-                                  "POPC (carry-save adders: 5 per 8 words; OR-fold lower-bound filter: 1 per word pair once the "
+                                  "POPC (carry-save adders: 5 per 8 words; OR-fold lower-bound filter: 1 per group of 2-3 words once the "
                                   "threshold is tight), so frac exceeds 1; xu_pipe_frac is the share of the POPC pipe actually issued",
                           "xu_pipe_frac": (issued_popc / (scan_ms * 1e-3)) / popc_peak if scan_ms > 0 else None,
                           "pairs_per_s": pairs / (scan_ms * 1e-3) if scan_ms > 0 else None,
