@@ -1,0 +1,671 @@
+"""
+Protocol backend: `B200Index` (one index) and `B200IndexManager` (IsccIndexProtocol).
+
+Drop-in for the reference's usearch backend - `UsearchIndex` (/root/reference/iscc_search/indexes/usearch/index.py:87-2045)
+and `UsearchIndexManager` (indexes/usearch/manager.py:26-335) - behind the same protocol
+(protocols/index.py:19-174): list/create/get/delete index, add_assets, get_asset, search_assets, close, with the
+same result models, status values, error types and message substrings. What changes is where the work happens:
+
+* similarity units   -> one HBM store per unit type (`ShardedNphdIndex`, exact NPHD top-k on the GPU)
+* INSTANCE units     -> `InstancePrefixIndex` (bidirectional prefix match as an `NPHD == 0` scan) instead of an LMDB dupsort table
+* simprints          -> `B200SimprintIndex` per simprint type: threshold search, exact equality join and document
+                        frequencies all answered by the same HBM store (the reference needs LMDB dupsort tables for the last two)
+* assets / metadata  -> `AssetLog` (host; the HBM stores are derived data, rebuilt from it when a snapshot is missing or stale)
+
+The host arithmetic that turns distances into scores and aggregates them is restated line by line from
+index.py:762-881 so that results are identical given identical neighbours. `search_assets_batch` is an extension:
+many queries, one GPU batch per unit type, results identical to sequential `search_assets` calls.
+"""
+
+import hashlib
+import shutil
+import struct
+import threading
+from pathlib import Path
+
+import numpy as np
+
+from iscc_search_b200 import entries
+from iscc_search_b200 import iscc as ic
+from iscc_search_b200.assetlog import AssetLog
+from iscc_search_b200.iscc import IsccID, IsccUnit
+from iscc_search_b200.simprint import pack_chunk_pointer
+
+DEFAULT_OPTIONS = {
+    # defaults of /root/reference/iscc_search/options.py:95-125
+    "match_threshold_units": 0.75,
+    "match_threshold_simprints": 0.75,
+    "confidence_exponent": 4,
+    "oversampling_factor": 20,
+    "flush_interval": 100000,
+}
+
+SP_FINGERPRINT_BYTES = 16
+
+
+def set_schema(module):
+    """Use another module's result classes (inside iscc-search: `set_schema(iscc_search.schema)`)."""
+    entries.schema = module
+
+
+class GpuStores:
+    """Factory of the HBM-resident stores of one index (the only product implementation: no CPU variant)."""
+
+    def __init__(self, device=0):
+        self.device = device
+
+    def nphd(self, max_dim, path):
+        from iscc_search_b200.nphd import ShardedNphdIndex
+
+        return ShardedNphdIndex(max_dim=max_dim, path=path, device=self.device)
+
+    def simprint(self, path, ndim, oversampling_factor):
+        from iscc_search_b200.simprint import B200SimprintIndex
+
+        return B200SimprintIndex(path=path, ndim=ndim, oversampling_factor=oversampling_factor, device=self.device)
+
+    def instance(self):
+        from iscc_search_b200.instance import InstancePrefixIndex
+
+        return InstancePrefixIndex(device=self.device)
+
+
+def simprint_fingerprint(simprints):
+    # type: (list) -> bytes
+    """Order-independent 16-byte digest of one type's (simprint, offset, size) entries - index.py:565-587."""
+    triples = sorted((ic.decode_base64(sp.simprint), sp.offset, sp.size) for sp in simprints)
+    hasher = hashlib.blake2b(digest_size=SP_FINGERPRINT_BYTES)
+    for sp_bytes, offset, size in triples:
+        hasher.update(struct.pack("!I", len(sp_bytes)))
+        hasher.update(sp_bytes)
+        hasher.update(struct.pack("!II", offset, size))
+    return hasher.digest()
+
+
+class B200Index:
+    """One index directory: asset log + HBM stores. Mirrors `UsearchIndex`."""
+
+    def __init__(self, path, realm_id=None, max_dim=256, device=0, stores=None, **options):
+        # type: (str | Path, int | None, int, int, object | None, object) -> None
+        unknown = set(options) - set(DEFAULT_OPTIONS)
+        if unknown:
+            raise ValueError(f"Unknown options: {sorted(unknown)}")
+        self._opts = dict(DEFAULT_OPTIONS, **options)
+        self.path = Path(path)
+        self._stores = stores if stores is not None else GpuStores(device)
+        self._log = AssetLog(self.path, realm_id=realm_id, max_dim=max_dim)
+        self.max_dim = self._log.max_dim
+        self._realm_id = self._log.realm_id
+        self._nphd_indexes = {}      # unit_type -> ShardedNphdIndex
+        self._simprint_indexes = {}  # sp_type -> B200SimprintIndex
+        self._instance = self._stores.instance()
+        self._write_lock = threading.RLock()
+        self._closed = False
+        self._load_derived()
+
+    # ---- derived stores: load snapshot, rebuild from the log when missing or stale (index.py:1602-1648, 1765-1827)
+    def _unit_rows(self):
+        """(unit_type -> {key: longest body}, [(key, INSTANCE body)]) from the asset log."""
+        best, instance = {}, []
+        for key, asset_bytes in self._log.assets.items():
+            for unit_str in entries.deserialize_asset(asset_bytes).units or []:
+                unit = IsccUnit(unit_str)
+                if unit.unit_type.startswith("INSTANCE_"):
+                    instance.append((key, unit.body))
+                else:
+                    rows = best.setdefault(unit.unit_type, {})
+                    if key not in rows or len(unit.body) > len(rows[key]):
+                        rows[key] = unit.body  # keep the longest body per key (index.py:1667-1685)
+        return best, instance
+
+    def _load_derived(self):
+        best, instance = self._unit_rows()
+        self._instance.add_many(instance)
+        for unit_type, rows in best.items():
+            index = self._stores.nphd(self.max_dim, self.path / unit_type)
+            if index.size != len(rows):  # snapshot missing or out of step with the log: rebuild
+                index.reset()
+                index = self._stores.nphd(self.max_dim, self.path / unit_type)
+                index.add(list(rows.keys()), list(rows.values()))
+                index.save()
+            self._nphd_indexes[unit_type] = index
+        for sp_type in self._log.simprints:
+            keys, vectors = self._simprint_rows(sp_type)
+            if not keys:
+                continue
+            sp_dir, ndim = self.path / f"SIMPRINT_{sp_type}", 8 * len(vectors[0])
+            index = self._stores.simprint(sp_dir, ndim, self._opts["oversampling_factor"])
+            if index.size != len(set(keys)):
+                index.reset()
+                index = self._stores.simprint(sp_dir, ndim, self._opts["oversampling_factor"])
+                index.add_raw(keys, vectors)
+                index.save()
+            self._simprint_indexes[sp_type] = index
+
+    @property
+    def tracked_unit_types(self):
+        return sorted(self._nphd_indexes)
+
+    @property
+    def tracked_simprint_types(self):
+        return sorted(self._simprint_indexes)
+
+    def rebuild(self, unit_types, simprint_types):
+        # type: (list[str], list[str]) -> dict[str, list[str]]
+        """Drop and rebuild the named derived stores from the asset log; types without rows are skipped (index.py:1058-1082)."""
+        with self._write_lock:
+            best, _instance = self._unit_rows()
+            rebuilt_units, rebuilt_sp = [], []
+            for unit_type in unit_types:
+                rows = best.get(unit_type)
+                if not rows:
+                    continue
+                old = self._nphd_indexes.pop(unit_type, None)
+                if old is not None:
+                    old.reset()
+                    old.close()
+                shutil.rmtree(self.path / unit_type, ignore_errors=True)
+                index = self._stores.nphd(self.max_dim, self.path / unit_type)
+                index.add(list(rows.keys()), list(rows.values()))
+                index.save()
+                self._nphd_indexes[unit_type] = index
+                rebuilt_units.append(unit_type)
+            for sp_type in simprint_types:
+                keys, vectors = self._simprint_rows(sp_type)
+                if not keys:
+                    continue
+                old = self._simprint_indexes.pop(sp_type, None)
+                if old is not None:
+                    old.reset()
+                    old.close()
+                shutil.rmtree(self.path / f"SIMPRINT_{sp_type}", ignore_errors=True)
+                index = self._stores.simprint(self.path / f"SIMPRINT_{sp_type}", 8 * len(vectors[0]), self._opts["oversampling_factor"])
+                index.add_raw(keys, vectors)
+                index.save()
+                self._simprint_indexes[sp_type] = index
+                rebuilt_sp.append(sp_type)
+            return {"unit_types": rebuilt_units, "simprint_types": rebuilt_sp}
+
+    def _simprint_rows(self, sp_type):
+        keys, vectors = [], []
+        for body, (_f, sp_entries) in (self._log.simprints.get(sp_type) or {}).items():
+            for sp_bytes, offset, size in sp_entries:
+                keys.append(pack_chunk_pointer(body, offset, size))
+                vectors.append(np.frombuffer(sp_bytes, dtype=np.uint8))
+        return keys, vectors
+
+    def _get_or_create_nphd_index(self, unit_type):
+        if unit_type not in self._nphd_indexes:
+            self._nphd_indexes[unit_type] = self._stores.nphd(self.max_dim, self.path / unit_type)
+        return self._nphd_indexes[unit_type]
+
+    def _get_or_create_simprint_index(self, sp_type, ndim):
+        if sp_type not in self._simprint_indexes:
+            self._simprint_indexes[sp_type] = self._stores.simprint(self.path / f"SIMPRINT_{sp_type}", ndim,
+                                                                      self._opts["oversampling_factor"])
+        return self._simprint_indexes[sp_type]
+
+    # ---- add (index.py:194-537)
+    def add_assets(self, assets):
+        # type: (list) -> list
+        if not assets:
+            return []
+        schema = entries.schema
+        results = []
+        with self._write_lock:
+            if self._realm_id is None:  # inferred from the first asset (index.py:239-252)
+                if assets[0].iscc_id is None:
+                    raise ValueError("Asset must have iscc_id field when adding to index")
+                self._realm_id = entries.extract_realm_id(assets[0].iscc_id)
+                self._log.set_realm(self._realm_id)
+
+            # validate the whole batch before the first mutation (the reference's LMDB transaction would roll back)
+            for asset in assets:
+                if asset.iscc_id is None:
+                    raise ValueError("Asset must have iscc_id field when adding to index")
+                asset_realm = entries.extract_realm_id(asset.iscc_id)
+                if self._realm_id != asset_realm:
+                    raise ValueError(
+                        f"Realm ID mismatch: index has realm={self._realm_id}, "
+                        f"but asset '{asset.iscc_id}' has realm={asset_realm}. "
+                        f"All assets in an index must have the same realm ID."
+                    )
+                for unit_str in asset.units or []:
+                    IsccUnit(unit_str).unit_type
+
+            nphd_batches = {}     # unit_type -> ([keys], [bodies])
+            nphd_updated_keys = set()
+            sp_batches = {}       # sp_type -> ([chunk pointers], [vectors])
+            sp_deleted_keys = {}  # sp_type -> [chunk pointers]
+            instance_add, instance_remove = [], []
+            last_occurrence = {asset.iscc_id: i for i, asset in enumerate(assets)}  # in-batch dedup, last wins (:263-265)
+            batch_seen = set()
+
+            for i, asset in enumerate(assets):
+                iscc_id_obj = IsccID(asset.iscc_id)
+                key = int(iscc_id_obj)
+                existing = self._log.assets.get(key)
+                status = schema.Status.updated if (existing or key in batch_seen) else schema.Status.created
+                batch_seen.add(key)
+                if i != last_occurrence[asset.iscc_id]:
+                    results.append(schema.IsccAddResult(iscc_id=asset.iscc_id, status=status))
+                    continue
+
+                asset_bytes = entries.serialize_asset(asset)
+                iscc_id_body = iscc_id_obj.body
+                sp_fingerprints = {t: simprint_fingerprint(lst) for t, lst in (asset.simprints or {}).items()}
+                # idempotent re-add: nothing to do when stored bytes, derived unit rows and simprints are all current (:294-327)
+                if (existing == asset_bytes and self._nphd_units_present(key, asset.units)
+                        and self._simprints_already_indexed(iscc_id_body, asset, sp_fingerprints)):
+                    results.append(schema.IsccAddResult(iscc_id=asset.iscc_id, status=status))
+                    continue
+                if existing:
+                    nphd_updated_keys.add(key)
+                    new_units = set(asset.units or [])
+                    for old_unit_str in entries.deserialize_asset(existing).units or []:
+                        if old_unit_str in new_units:
+                            continue
+                        old_unit = IsccUnit(old_unit_str)
+                        if old_unit.unit_type.startswith("INSTANCE_"):  # stale INSTANCE bodies go (:339-348)
+                            instance_remove.append((key, old_unit.body))
+
+                self._log.put_asset(key, asset_bytes)
+
+                for unit_str in asset.units or []:
+                    unit = IsccUnit(unit_str)
+                    if unit.unit_type.startswith("INSTANCE_"):
+                        instance_add.append((key, unit.body))
+                    else:
+                        batch = nphd_batches.setdefault(unit.unit_type, ([], []))
+                        batch[0].append(key)
+                        batch[1].append(unit.body)
+
+                for sp_type, sp_list in (asset.simprints or {}).items():
+                    table = self._log.simprints.get(sp_type) or {}
+                    if iscc_id_body in table:  # update: old chunk pointers leave the derived store (:379-383)
+                        old_entries = table[iscc_id_body][1]
+                        sp_deleted_keys.setdefault(sp_type, []).extend(
+                            pack_chunk_pointer(iscc_id_body, o, z) for _s, o, z in old_entries)
+                    new_entries = []
+                    batch = sp_batches.setdefault(sp_type, ([], []))
+                    for sp_obj in sp_list:
+                        sp_bytes = ic.decode_base64(sp_obj.simprint)
+                        new_entries.append((sp_bytes, sp_obj.offset, sp_obj.size))
+                        batch[0].append(pack_chunk_pointer(iscc_id_body, sp_obj.offset, sp_obj.size))
+                        batch[1].append(np.frombuffer(sp_bytes, dtype=np.uint8))
+                    self._log.put_simprints(sp_type, iscc_id_body, sp_fingerprints[sp_type], new_entries)
+
+                results.append(schema.IsccAddResult(iscc_id=asset.iscc_id, status=status))
+
+            self._log.commit()  # host log first, derived stores after (same order as LMDB commit -> usearch, :407-410)
+
+            self._instance.remove_many(instance_remove)
+            self._instance.add_many(instance_add)
+
+            for unit_type, (keys, vectors) in nphd_batches.items():
+                nphd_index = self._get_or_create_nphd_index(unit_type)
+                if len(keys) != len(set(keys)):  # one key, two lengths of a unit type: the last one stays (:420-430)
+                    unique = {}
+                    for k, v in zip(keys, vectors):
+                        unique[k] = v
+                    keys, vectors = list(unique.keys()), list(unique.values())
+                keys_to_remove = [k for k in keys if k in nphd_updated_keys]
+                if keys_to_remove:
+                    nphd_index.remove(keys_to_remove)
+                nphd_index.add(keys, vectors)
+
+            for sp_type, (composite_keys, sp_vectors) in sp_batches.items():
+                sp_index = self._get_or_create_simprint_index(sp_type, len(sp_vectors[0]) * 8)
+                if sp_type in sp_deleted_keys:
+                    sp_index.remove(sp_deleted_keys[sp_type])
+                sp_index.add_raw(composite_keys, sp_vectors)
+
+            flush_interval = self._opts["flush_interval"]
+            if flush_interval > 0:
+                for index in list(self._nphd_indexes.values()) + list(self._simprint_indexes.values()):
+                    if index.dirty >= flush_interval:
+                        index.save()
+        return results
+
+    def _nphd_units_present(self, key, units):
+        for unit_str in units or []:
+            unit_type = IsccUnit(unit_str).unit_type
+            if unit_type.startswith("INSTANCE_"):
+                continue
+            nphd_index = self._nphd_indexes.get(unit_type)
+            if nphd_index is None or key not in nphd_index:
+                return False
+        return True
+
+    def _simprints_already_indexed(self, iscc_id_body, asset, fingerprints):
+        """Subset semantics of index.py:589-655: every incoming type is stored with the same fingerprint and its rows exist."""
+        for sp_type, sp_list in (asset.simprints or {}).items():
+            stored = (self._log.simprints.get(sp_type) or {}).get(iscc_id_body)
+            if stored is None or stored[0] != fingerprints[sp_type]:
+                return False
+            sp_index = self._simprint_indexes.get(sp_type)
+            if sp_index is None:
+                return False
+            for sp_obj in sp_list:
+                if pack_chunk_pointer(iscc_id_body, sp_obj.offset, sp_obj.size) not in sp_index:
+                    return False
+        return True
+
+    # ---- get (index.py:704-733)
+    def get_asset(self, iscc_id):
+        entries.validate_iscc_id(iscc_id, expected_realm=self._realm_id)
+        asset_bytes = self._log.assets.get(int(IsccID(iscc_id)))
+        if asset_bytes is None:
+            raise FileNotFoundError(f"Asset '{iscc_id}' not found in index")
+        return entries.deserialize_asset(asset_bytes)
+
+    # ---- search (index.py:735-881)
+    def search_assets(self, query, limit=100, exact=False):
+        return self.search_assets_batch([query], limit, exact)[0]
+
+    def search_assets_batch(self, queries, limit=100, exact=False):
+        # type: (list, int, bool) -> list
+        """Many queries at once: one GPU batch per unit type; each result equals `search_assets(query)`."""
+        schema = entries.schema
+        prepared = []
+        for query in queries:
+            query_iscc_id = None
+            if query.iscc_id:  # look-up + self-exclusion (:762-769)
+                query_iscc_id = query.iscc_id
+                asset = self.get_asset(query.iscc_id)
+                query = schema.IsccQuery(iscc_code=asset.iscc_code, units=asset.units, simprints=_as_query_simprints(asset.simprints))
+            prepared.append((entries.normalize_query(query), query_iscc_id))
+
+        # similarity units of all queries, grouped per unit type -> one batched exact NPHD top-k each
+        wanted = {}  # unit_type -> [(query index, body)]
+        for qi, (query, _qid) in enumerate(prepared):
+            for unit_str in query.units or []:
+                unit = IsccUnit(unit_str)
+                if not unit.unit_type.startswith("INSTANCE_") and unit.unit_type in self._nphd_indexes:
+                    wanted.setdefault(unit.unit_type, []).append((qi, unit.body))
+        similar = {}  # (query index, unit_type, body) -> {key: score}
+        for unit_type, items in wanted.items():
+            bodies = list(dict.fromkeys(body for _qi, body in items))
+            for body, scores in zip(bodies, self._search_similarity_units(unit_type, bodies, limit)):
+                for qi, b in items:
+                    if b == body:
+                        similar[(qi, unit_type, body)] = scores
+
+        out = []
+        for qi, (query, query_iscc_id) in enumerate(prepared):
+            chunk_matches = []
+            if self._simprint_indexes and query.simprints:
+                chunk_matches = self._search_simprints(query, limit, exact=exact)
+            matches = []
+            if query.units:
+                aggregated = {}  # key -> {unit_type: score}
+                for unit_str in query.units:
+                    unit = IsccUnit(unit_str)
+                    unit_type = unit.unit_type
+                    if unit_type.startswith("INSTANCE_"):
+                        for key, score in self._instance.search(unit.body).items():
+                            aggregated.setdefault(key, {})[unit_type] = score
+                    elif unit_type in self._nphd_indexes:
+                        for key, score in similar[(qi, unit_type, unit.body)].items():
+                            per_type = aggregated.setdefault(key, {})
+                            per_type[unit_type] = max(per_type.get(unit_type, 0.0), score)
+
+                threshold, exponent = self._opts["match_threshold_units"], self._opts["confidence_exponent"]
+                scored_results = []
+                for key, unit_scores in aggregated.items():
+                    confident = {t: s for t, s in unit_scores.items() if s >= threshold}
+                    if not confident:
+                        continue
+                    weighted_sum = sum(s**exponent for s in confident.values())
+                    weight_sum = sum(s for s in confident.values())
+                    total_score = weighted_sum / weight_sum if weight_sum > 0 else 0.0
+                    scored_results.append((key, total_score, unit_scores))
+                if query_iscc_id:
+                    query_key = int(IsccID(query_iscc_id))
+                    scored_results = [r for r in scored_results if r[0] != query_key]
+                scored_results.sort(key=lambda x: x[1], reverse=True)
+                scored_results = scored_results[:limit]
+                for key, total_score, unit_scores in scored_results:
+                    metadata = None
+                    asset_bytes = self._log.assets.get(key)
+                    if asset_bytes is not None:
+                        asset = entries.deserialize_asset(asset_bytes)
+                        if asset.metadata:
+                            metadata = asset.metadata
+                    matches.append(schema.IsccGlobalMatch(iscc_id=str(IsccID.from_int(key, self._realm_id)), score=total_score,
+                                                          types=unit_scores, metadata=metadata))
+            if query_iscc_id:
+                chunk_matches = [m for m in chunk_matches if m.iscc_id != query_iscc_id]
+            out.append(schema.IsccSearchResult(query=query, global_matches=matches, chunk_matches=chunk_matches))
+        return out
+
+    def _search_similarity_units(self, unit_type, bodies, limit):
+        # type: (str, list[bytes], int) -> list[dict[int, float]]
+        """Batched `_search_similarity_unit` (index.py:2024-2045): score = max(0, 1 - float(float32 NPHD))."""
+        nphd_index = self._nphd_indexes[unit_type]
+        if nphd_index.size == 0:
+            return [{} for _ in bodies]
+        count = min(int(limit), getattr(nphd_index, "max_count", int(limit)))  # REST `limit` is unbounded above (server/search.py:22)
+        res = nphd_index.search([np.frombuffer(b, dtype=np.uint8) for b in bodies], count=count)
+        per_query = [res] if len(bodies) == 1 else [res[i] for i in range(len(bodies))]
+        out = []
+        for m in per_query:
+            scores = {}
+            for key, distance in zip(m.keys, m.distances):
+                scores[int(key)] = max(0.0, 1.0 - float(distance))
+            out.append(scores)
+        return out
+
+    def _search_instance_unit(self, instance_code):
+        return self._instance.search(instance_code)
+
+    def _search_similarity_unit(self, unit_type, vector, limit):
+        return self._search_similarity_units(unit_type, [vector], limit)[0]
+
+    # ---- simprints (index.py:1084-1469)
+    def _search_simprints(self, query, limit, exact=False):
+        from iscc_search_b200.simprint import SimprintMatchMulti, TypeMatchResult
+
+        total_assets = len(self._log.assets)
+        threshold = self._opts["match_threshold_simprints"]
+        asset_type_results = {}  # iscc_id_body -> {sp_type: TypeMatchResult}
+        for sp_type, simprint_objs in query.simprints.items():
+            sp_index = self._simprint_indexes.get(sp_type)
+            if sp_index is None:
+                continue
+            query_sp_bytes = [ic.decode_base64(s.root if hasattr(s, "root") else s) for s in simprint_objs]
+            if exact:
+                type_total = len(self._log.simprints.get(sp_type) or {})
+                raw_matches = sp_index.search_exact(query_sp_bytes, total_assets=type_total, limit=limit * 2,
+                                                    threshold=threshold, detailed=True)
+            else:
+                raw_matches = sp_index.search_raw(simprints=query_sp_bytes, limit=limit * 2, threshold=threshold, detailed=True,
+                                                  doc_freq_fn="index", total_assets=total_assets)
+            for raw in raw_matches:
+                asset_type_results.setdefault(raw.iscc_id_body, {})[sp_type] = TypeMatchResult(
+                    score=raw.score, queried=raw.queried, matches=raw.matches, chunks=raw.chunks)
+        if not asset_type_results:
+            return []
+        multi = []
+        for iscc_id_body, type_results in asset_type_results.items():
+            asset_score = sum(tr.score for tr in type_results.values()) / len(type_results)
+            multi.append(SimprintMatchMulti(iscc_id=IsccID.from_body(iscc_id_body, self._realm_id).digest, score=asset_score,
+                                            types=type_results))
+        multi.sort(key=lambda x: (-x.score, x.iscc_id))
+        return [self._convert_simprint_match(m) for m in multi[:limit]]
+
+    def _convert_simprint_match(self, raw_match):
+        """Bytes -> strings + metadata enrichment (index.py:1101-1163)."""
+        schema = entries.schema
+        source, metadata = None, None
+        asset_bytes = self._log.assets.get(int.from_bytes(raw_match.iscc_id[2:], "big", signed=False))
+        if asset_bytes is not None:
+            asset = entries.deserialize_asset(asset_bytes)
+            if asset.metadata:
+                source, metadata = asset.metadata.get("source"), asset.metadata
+        types_converted = {}
+        for sp_type, tr in raw_match.types.items():
+            chunks = None
+            if tr.chunks is not None:
+                chunks = [schema.IsccMatchedChunk(query=ic.encode_base64(c.query), match=ic.encode_base64(c.match), score=c.score,
+                                                  freq=c.freq, offset=c.offset, size=c.size, content=None) for c in tr.chunks]
+            types_converted[sp_type] = schema.Types(score=tr.score, matches=tr.matches, queried=tr.queried, chunks=chunks)
+        return schema.IsccChunkMatch(iscc_id="ISCC:" + ic.encode_base32(raw_match.iscc_id), score=raw_match.score,
+                                     types=types_converted, source=source, metadata=metadata)
+
+    # ---- bookkeeping (index.py:883-1056)
+    def flush(self):
+        with self._write_lock:
+            self._log.commit()
+            for index in list(self._nphd_indexes.values()) + list(self._simprint_indexes.values()):
+                if index.dirty:
+                    index.save()
+
+    def close(self):
+        if self._closed:
+            return
+        with self._write_lock:
+            if self._closed:
+                return
+            for index in list(self._nphd_indexes.values()) + list(self._simprint_indexes.values()):
+                try:
+                    if index.dirty:
+                        index.save()
+                    index.close()
+                except Exception:  # pragma: no cover - one failing store must not keep the others from saving
+                    pass
+            self._nphd_indexes.clear()
+            self._simprint_indexes.clear()
+            self._instance.close()
+            self._log.close()
+            self._closed = True
+
+    def __len__(self):
+        return len(self._log.assets)
+
+    @property
+    def derived_sizes(self):
+        # type: () -> dict[str, int]
+        sizes = {t: int(ix.serialized_length) for t, ix in self._nphd_indexes.items()}
+        for sp_type, sp_index in self._simprint_indexes.items():
+            sizes[f"SIMPRINT_{sp_type}"] = int(sp_index.data_size)
+        return sizes
+
+
+def _as_query_simprints(simprints):
+    """Entry simprints ({type: [IsccSimprint]}) -> query form ({type: [base64 str]}), as IsccQuery's validation does."""
+    if not simprints:
+        return None
+    return {t: [s.simprint if hasattr(s, "simprint") else s for s in lst] for t, lst in simprints.items()}
+
+
+class B200IndexManager:
+    """IsccIndexProtocol over a directory of `B200Index` sub-directories. Mirrors `UsearchIndexManager`."""
+
+    MARKER = AssetLog.META
+
+    def __init__(self, base_path, max_dim=256, device=0, stores=None, **options):
+        self.base_path = Path(base_path)
+        self.base_path.mkdir(parents=True, exist_ok=True)
+        self.max_dim = max_dim
+        self._device, self._stores, self._options = device, stores, options
+        self._index_cache = {}
+        self._cache_lock = threading.Lock()
+
+    def list_indexes(self):
+        schema = entries.schema
+        found = []
+        for index_dir in self.base_path.iterdir():
+            if not index_dir.is_dir() or not (index_dir / self.MARKER).exists():
+                continue
+            try:
+                idx = self._get_or_load_index(index_dir.name)
+                size_mb, sizes_mb = self._get_index_sizes_mb(idx)
+                found.append(schema.IsccIndex(name=index_dir.name, assets=len(idx), size=size_mb, sizes=sizes_mb))
+            except Exception:  # corrupted or inaccessible index: skipped, like manager.py:83-86
+                continue
+        found.sort(key=lambda x: x.name)
+        return found
+
+    def create_index(self, index):
+        entries.validate_index_name(index.name)
+        index_path = self.base_path / index.name
+        if index_path.exists():
+            raise FileExistsError(f"Index '{index.name}' already exists")
+        try:
+            self._index_cache[index.name] = self._open(index_path)
+        except Exception:
+            shutil.rmtree(index_path, ignore_errors=True)  # e.g. no CUDA device: leave no half-created index behind
+            raise
+        return entries.schema.IsccIndex(name=index.name, assets=0, size=0)
+
+    def get_index(self, name):
+        self._validate_index_exists(name)
+        idx = self._get_or_load_index(name)
+        size_mb, sizes_mb = self._get_index_sizes_mb(idx)
+        return entries.schema.IsccIndex(name=name, assets=len(idx), size=size_mb, sizes=sizes_mb)
+
+    def delete_index(self, name):
+        self._validate_index_exists(name)
+        if name in self._index_cache:
+            self._index_cache[name].close()
+            del self._index_cache[name]
+        shutil.rmtree(self.base_path / name)
+
+    def add_assets(self, index_name, assets):
+        self._validate_index_exists(index_name)
+        return self._get_or_load_index(index_name).add_assets(assets)
+
+    def get_asset(self, index_name, iscc_id):
+        self._validate_index_exists(index_name)
+        return self._get_or_load_index(index_name).get_asset(iscc_id)
+
+    def search_assets(self, index_name, query, limit=100):
+        self._validate_index_exists(index_name)
+        return self._get_or_load_index(index_name).search_assets(query, limit)
+
+    def search_assets_batch(self, index_name, queries, limit=100):
+        self._validate_index_exists(index_name)
+        return self._get_or_load_index(index_name).search_assets_batch(queries, limit)
+
+    def rebuild(self, name, unit_types=None, simprint_types=None):
+        self._validate_index_exists(name)
+        idx = self._get_or_load_index(name)
+        if unit_types is None:
+            unit_types = idx.tracked_unit_types
+        if simprint_types is None:
+            simprint_types = idx.tracked_simprint_types
+        return idx.rebuild(unit_types, simprint_types)
+
+    def close(self):
+        for _name, idx in list(self._index_cache.items()):
+            try:
+                idx.close()
+            except Exception:  # pragma: no cover
+                pass
+        self._index_cache = {}
+
+    # -- helpers
+    def _open(self, index_path):
+        return B200Index(index_path, realm_id=None, max_dim=self.max_dim, device=self._device, stores=self._stores, **self._options)
+
+    def _get_or_load_index(self, name):
+        if name in self._index_cache:
+            return self._index_cache[name]
+        with self._cache_lock:
+            if name not in self._index_cache:
+                self._index_cache[name] = self._open(self.base_path / name)
+            return self._index_cache[name]
+
+    def _validate_index_exists(self, name):
+        if not (self.base_path / name / self.MARKER).exists():
+            raise FileNotFoundError(f"Index '{name}' not found")
+
+    @staticmethod
+    def _get_index_sizes_mb(idx):
+        # type: (B200Index) -> tuple[int, dict[str, int]]
+        """(total MB, per-component MB); component "lmdb" names the host log for compatibility with manager.py:296-335."""
+        component_bytes = {"lmdb": idx._log.used_bytes()}
+        component_bytes.update(idx.derived_sizes)
+        mb = 1024 * 1024
+        return sum(component_bytes.values()) // mb, {name: size // mb for name, size in component_bytes.items()}

@@ -6,60 +6,92 @@ prefix match, every hit scoring 1.0 (/root/reference/iscc_search/indexes/usearch
 A stored code and a query match bidirectionally iff their common byte prefix is identical, i.e. iff the
 prefix Hamming distance is 0 - exactly the store's threshold match with thr = 0/1 (`isx_match_all`,
 unbounded output). One asset may carry INSTANCE units of several lengths (index.py:363-366 puts one dupsort
-entry per unit), so rows are keyed by (ISCC-ID, length) in a 128-bit-key store.
+entry per unit), so rows are keyed by (ISCC-ID, length, digest of the body) in a 128-bit-key store.
 
 Parity nuance kept on purpose: the reference's reverse direction only probes the 128- and 64-bit prefixes of
 the query (index.py:1989, 2003-2020), so a stored 192-bit body that prefixes a 256-bit query is NOT a hit there;
 `search` drops those rows (their compared length is visible in `nbits`).
 """
 
+import hashlib
 import struct
 
 import numpy as np
 
-from iscc_search_b200._lib import Store
+
+def _default_store(device):
+    from iscc_search_b200._lib import Store
+
+    return Store(device=device, key_bytes=16, max_bytes=32, fixed_len=0)
 
 
 class InstancePrefixIndex:
     """HBM-resident replacement for the `__instance__` dupsort table: add / remove / bidirectional prefix search."""
 
-    def __init__(self, device=0):
-        self._store = Store(device=device, key_bytes=16, max_bytes=32, fixed_len=0)
+    def __init__(self, device=0, store=None):
+        self._store = store if store is not None else _default_store(device)
 
     @staticmethod
-    def _key(iscc_id_key, nbytes):
-        return struct.pack(">QQ", int(iscc_id_key), nbytes)
+    def _key(iscc_id_key, code):
+        # (ISCC-ID, body) pairs are unique in the dupsort table (index.py:365-366, dupdata=False): the row key is the
+        # ISCC-ID followed by the body length and a 56-bit digest of the body
+        return struct.pack(">QB", int(iscc_id_key), len(code)) + hashlib.blake2b(code, digest_size=7).digest()
+
+    def _rows(self, pairs):
+        n = len(pairs)
+        keys = np.zeros((n, 16), dtype=np.uint8)
+        codes = np.zeros((n, 32), dtype=np.uint8)
+        lens = np.zeros(n, dtype=np.uint8)
+        for i, (iscc_id_key, code) in enumerate(pairs):
+            code = bytes(code)
+            if not 1 <= len(code) <= 32:
+                raise ValueError(f"INSTANCE body must be 1..32 bytes, got {len(code)}")
+            keys[i] = np.frombuffer(self._key(iscc_id_key, code), dtype=np.uint8)
+            codes[i, : len(code)] = np.frombuffer(code, dtype=np.uint8)
+            lens[i] = len(code)
+        return keys, codes, lens
 
     def add(self, iscc_id_key, instance_code):
         # type: (int, bytes) -> None
         """Register one INSTANCE unit body (8/16/32 bytes) of the asset with integer ISCC-ID key (index.py:363-366)."""
-        code = bytes(instance_code)
-        codes = np.zeros((1, 32), dtype=np.uint8)
-        codes[0, : len(code)] = np.frombuffer(code, dtype=np.uint8)
-        key = np.frombuffer(self._key(iscc_id_key, len(code)), dtype=np.uint8).reshape(1, 16).copy()
-        self._store.add(key, codes, np.array([len(code)], dtype=np.uint8))
+        self.add_many([(iscc_id_key, instance_code)])
 
-    def remove_asset(self, iscc_id_key):
-        # type: (int) -> int
-        """Drop every INSTANCE unit of an asset (update path: remove-before-add, index.py:433-437)."""
-        keys = np.stack([np.frombuffer(self._key(iscc_id_key, n), dtype=np.uint8) for n in range(1, 33)]).copy()
+    def add_many(self, pairs):
+        # type: (list[tuple[int, bytes]]) -> None
+        """One batched add of (ISCC-ID key, body) pairs; pairs already present are skipped (dupdata=False)."""
+        if pairs:
+            self._store.add(*self._rows(pairs))
+
+    def remove(self, iscc_id_key, instance_code):
+        # type: (int, bytes) -> int
+        """Drop one (ISCC-ID, body) row - the update path's stale-body delete (index.py:339-348)."""
+        return self.remove_many([(iscc_id_key, instance_code)])
+
+    def remove_many(self, pairs):
+        # type: (list[tuple[int, bytes]]) -> int
+        if not pairs:
+            return 0
+        keys, _codes, _lens = self._rows(pairs)
         return self._store.remove(keys, len(keys))[1]
 
     def search(self, instance_code):
         # type: (bytes) -> dict[int, float]
-        """Same return shape as `_search_instance_unit`: {ISCC-ID key: 1.0} for every bidirectional prefix match."""
+        """
+        Same return shape as `_search_instance_unit`: {ISCC-ID key: 1.0} for every bidirectional prefix match.
+        Insertion order of the dict is ascending ISCC-ID (deterministic; the reference's is LMDB cursor order).
+        """
         code = bytes(instance_code)
         keys, _h, nbits = self._store.match_all(code, thr=(0, 1))
-        results = {}
         qbits = 8 * len(code)
+        hits = set()
         for k, n in zip(keys, nbits):
             n = int(n)
             # forward hits compare the whole query (n == qbits); reverse hits compare a shorter stored body:
             # the reference only probes 128- and 64-bit stored prefixes (index.py:2003-2020)
             if n < qbits and n not in (64, 128):
                 continue
-            results[struct.unpack(">Q", bytes(k[:8]))[0]] = 1.0
-        return results
+            hits.add(struct.unpack(">Q", bytes(k[:8]))[0])
+        return {key: 1.0 for key in sorted(hits)}
 
     def __len__(self):
         return self._store.size()

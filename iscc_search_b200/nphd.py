@@ -100,6 +100,11 @@ class _IndexBase:
         return self._dirty
 
     @property
+    def max_count(self):
+        """Largest `count` one search accepts (isx_max_k)."""
+        return self._store.max_k()
+
+    @property
     def shard_count(self):
         """No file shards: the store is one HBM-resident unit (0 when empty)."""
         return 1 if self._store.size() else 0

@@ -31,3 +31,13 @@ def cuda():
     if not _cuda_available():
         pytest.fail("gpu test selected but no CUDA device / libisx_b200.so available (no CPU fallback exists)")
     return True
+
+
+@pytest.fixture
+def cpu_stores(monkeypatch):
+    """Host layers above the C ABI on the oracle-backed store double (tests/fakes.py) - CPU tests of host logic only."""
+    from tests import fakes
+
+    monkeypatch.setattr("iscc_search_b200.nphd.Store", fakes.OracleStore)
+    monkeypatch.setattr("iscc_search_b200.instance._default_store", lambda device: fakes.OracleStore(device, 16, 32, 0))
+    return fakes.OracleStore

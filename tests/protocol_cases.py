@@ -1,0 +1,169 @@
+"""
+Protocol-level cases shared by the CPU suite (oracle-backed store double) and the GPU suite (real HBM stores).
+Modelled on the reference's cross-backend conformance tests: tests/test_indexes_usearch_manager.py,
+tests/test_indexes_usearch_index.py, tests/test_protocols_index.py, tests/test_server_*.py (message substrings).
+"""
+
+import numpy as np
+import pytest
+from pydantic import ValidationError
+
+from iscc_search_b200 import iscc as ic
+from iscc_search_b200.backend import B200IndexManager
+from iscc_search_b200.schema import IsccEntry, IsccIndex, IsccQuery, Status
+
+
+def unit(mt, st, body):
+    return "ISCC:" + ic.encode_base32(ic.encode_header(mt, st, 0, ic.encode_length(mt, len(body) * 8)) + body)
+
+
+def iscc_id(i, realm=0):
+    return ic.gen_iscc_id(timestamp=1_000_000 + i, hub_id=i % 4096, realm_id=realm)["iscc"]
+
+
+def flip(body, positions):
+    bits = np.unpackbits(np.frombuffer(body, dtype=np.uint8))
+    bits[list(positions)] ^= 1
+    return np.packbits(bits).tobytes()
+
+
+def rnd(seed, n):
+    return bytes(np.random.default_rng(seed).integers(0, 256, size=n, dtype=np.uint8))
+
+
+def case_index_lifecycle(tmp_path):
+    m = B200IndexManager(tmp_path)
+    assert m.list_indexes() == []
+    created = m.create_index(IsccIndex(name="test"))
+    assert (created.name, created.assets, created.size) == ("test", 0, 0)
+    assert (tmp_path / "test").is_dir()
+    with pytest.raises(FileExistsError, match="already exists"):
+        m.create_index(IsccIndex(name="test"))
+    with pytest.raises(ValidationError, match="String should match pattern"):
+        IsccIndex(name="Invalid-Name")
+    with pytest.raises(ValueError, match="Invalid index name"):
+        m.create_index(IsccIndex.model_construct(name="Invalid-Name"))
+    got = m.get_index("test")
+    assert got.name == "test" and got.assets == 0 and got.size >= 0 and "lmdb" in got.sizes
+    with pytest.raises(FileNotFoundError, match="not found"):
+        m.get_index("ghost")
+    m.create_index(IsccIndex(name="alpha"))
+    assert [i.name for i in m.list_indexes()] == ["alpha", "test"]
+    (tmp_path / "notanindex").mkdir()           # directories without the marker file and plain files are skipped
+    (tmp_path / "file.txt").write_text("x")
+    assert [i.name for i in m.list_indexes()] == ["alpha", "test"]
+    m.delete_index("alpha")
+    assert not (tmp_path / "alpha").exists()
+    with pytest.raises(FileNotFoundError, match="not found"):
+        m.delete_index("alpha")
+    for call in (lambda: m.add_assets("ghost", []), lambda: m.get_asset("ghost", iscc_id(1)),
+                 lambda: m.search_assets("ghost", IsccQuery(units=[unit(ic.MT.DATA, 0, bytes(8))])), lambda: m.rebuild("ghost")):
+        with pytest.raises(FileNotFoundError, match="not found"):
+            call()
+    m.close()
+    m.close()  # idempotent
+
+
+def case_add_get_search(tmp_path):
+    m = B200IndexManager(tmp_path)
+    m.create_index(IsccIndex(name="test"))
+    content, inst = rnd(1, 32), rnd(2, 32)
+    a = IsccEntry(iscc_id=iscc_id(1), units=[unit(ic.MT.CONTENT, 0, content), unit(ic.MT.INSTANCE, 0, inst[:16])],
+                  metadata={"name": "a", "source": "https://example.com/a"})
+    b = IsccEntry(iscc_id=iscc_id(2), units=[unit(ic.MT.CONTENT, 0, flip(content, [3, 77, 200])), unit(ic.MT.INSTANCE, 0, rnd(3, 16))])
+    c = IsccEntry(iscc_id=iscc_id(3), units=[unit(ic.MT.CONTENT, 0, rnd(4, 32)), unit(ic.MT.INSTANCE, 0, inst)])
+    assert m.search_assets("test", IsccQuery(units=a.units)).global_matches == []      # empty index
+    res = m.add_assets("test", [a, b, c])
+    assert [(r.iscc_id, r.status) for r in res] == [(a.iscc_id, Status.created), (b.iscc_id, Status.created), (c.iscc_id, Status.created)]
+    assert m.get_index("test").assets == 3
+    assert m.get_asset("test", a.iscc_id) == a
+    missing = iscc_id(99)
+    with pytest.raises(FileNotFoundError, match="not found") as ei:
+        m.get_asset("test", missing)
+    assert missing in str(ei.value)
+    with pytest.raises(ValueError, match="Realm mismatch"):
+        m.get_asset("test", iscc_id(1, realm=1))
+    with pytest.raises(ValueError, match="iscc_id"):
+        m.add_assets("test", [IsccEntry(units=a.units)])
+    with pytest.raises(ValueError, match="Realm ID mismatch"):
+        m.add_assets("test", [IsccEntry(iscc_id=iscc_id(5, realm=1), units=a.units)])
+    assert m.get_index("test").assets == 3                                            # failed batches leave nothing behind
+
+    r = m.search_assets("test", IsccQuery(units=a.units), limit=10)
+    # a and c both aggregate to 1.0 (stable sort keeps a first: it entered the aggregation first), b follows
+    assert [g.iscc_id for g in r.global_matches] == [a.iscc_id, c.iscc_id, b.iscc_id]
+    top = r.global_matches[0]
+    assert top.score == 1.0 and top.types == {"CONTENT_TEXT_V0": 1.0, "INSTANCE_NONE_V0": 1.0} and top.metadata.name == "a"
+    # b: only the CONTENT unit is near (3 of 256 bits differ); float32 NPHD turned into a Python float like the reference does
+    s_b = 1.0 - float(np.float32(3) / np.float32(256))
+    assert r.global_matches[2].types == {"CONTENT_TEXT_V0": s_b} and r.global_matches[2].score == s_b**4 / s_b
+    # c: INSTANCE prefix relation only (128-bit stored in a, 256-bit stored in c share a prefix): binary 1.0; its random
+    # CONTENT unit is reported in `types` unfiltered but does not enter the aggregate (below match_threshold_units)
+    assert r.global_matches[1].types["INSTANCE_NONE_V0"] == 1.0 and r.global_matches[1].score == 1.0
+    assert r.global_matches[1].types["CONTENT_TEXT_V0"] < 0.75
+
+    # ISCC-ID query: lookup + self exclusion; unknown id -> FileNotFoundError naming the id
+    r = m.search_assets("test", IsccQuery(iscc_id=a.iscc_id))
+    assert [g.iscc_id for g in r.global_matches] == [c.iscc_id, b.iscc_id] and r.query.units == a.units
+    with pytest.raises(FileNotFoundError) as ei:
+        m.search_assets("test", IsccQuery(iscc_id=missing))
+    assert missing in str(ei.value)
+    with pytest.raises(ValueError, match="Query must have"):
+        m.search_assets("test", IsccQuery())
+    # limit
+    assert len(m.search_assets("test", IsccQuery(units=a.units), limit=1).global_matches) == 1
+
+    # update: same id, new units -> status updated, old vectors and INSTANCE rows gone
+    a2 = IsccEntry(iscc_id=a.iscc_id, units=[unit(ic.MT.CONTENT, 0, rnd(7, 32)), unit(ic.MT.INSTANCE, 0, rnd(8, 16))])
+    assert [r.status for r in m.add_assets("test", [a2, a2])] == [Status.updated, Status.updated]
+    assert m.get_index("test").assets == 3 and m.get_asset("test", a.iscc_id) == a2
+    r = m.search_assets("test", IsccQuery(units=a.units), limit=10)
+    assert [g.iscc_id for g in r.global_matches][:2] == [c.iscc_id, b.iscc_id]
+    assert all(g.iscc_id != a.iscc_id or g.score < 1.0 for g in r.global_matches)
+    # idempotent re-add of identical bytes: still "updated", nothing changes
+    assert [r.status for r in m.add_assets("test", [a2])] == [Status.updated]
+
+    # batch front door: identical to sequential calls
+    qs = [IsccQuery(units=a.units), IsccQuery(units=b.units), IsccQuery(iscc_id=c.iscc_id), IsccQuery(units=a2.units[:1])]
+    assert m.search_assets_batch("test", qs, limit=10) == [m.search_assets("test", q, limit=10) for q in qs]
+    m.close()
+
+
+def case_persistence_and_rebuild(tmp_path):
+    m = B200IndexManager(tmp_path)
+    m.create_index(IsccIndex(name="keep"))
+    sp = [rnd(20 + i, 8) for i in range(3)]
+    entries_ = []
+    for i in range(12):
+        e = {"iscc_id": iscc_id(100 + i), "units": [unit(ic.MT.DATA, 0, flip(rnd(50, 16), range(i))), unit(ic.MT.INSTANCE, 0, rnd(60 + i, 8))]}
+        if i % 2 == 0:
+            e["simprints"] = {"CONTENT_TEXT_V0": [{"simprint": ic.encode_base64(s), "offset": 10 * j, "size": 10} for j, s in enumerate(sp)]}
+        entries_.append(IsccEntry(**e))
+    m.add_assets("keep", entries_)
+    q_units = IsccQuery(units=[unit(ic.MT.DATA, 0, rnd(50, 16))])
+    q_sp = IsccQuery(simprints={"CONTENT_TEXT_V0": [ic.encode_base64(s) for s in sp]})
+    before = (m.search_assets("keep", q_units), m.search_assets("keep", q_sp))
+    assert len(before[0].global_matches) == 12 and len(before[1].chunk_matches) == 6
+    assert before[1].chunk_matches[0].score == 1.0 and before[1].chunk_matches[0].types["CONTENT_TEXT_V0"].matches == 3
+    sizes = m.get_index("keep").sizes
+    assert set(sizes) == {"lmdb", "DATA_NONE_V0", "SIMPRINT_CONTENT_TEXT_V0"}
+    m.close()
+
+    m = B200IndexManager(tmp_path)  # re-open: snapshots + log
+    assert m.get_index("keep").assets == 12
+    assert (m.search_assets("keep", q_units), m.search_assets("keep", q_sp)) == before
+    idx = m._get_or_load_index("keep")
+    assert idx.tracked_unit_types == ["DATA_NONE_V0"] and idx.tracked_simprint_types == ["CONTENT_TEXT_V0"]
+    assert m.rebuild("keep") == {"unit_types": ["DATA_NONE_V0"], "simprint_types": ["CONTENT_TEXT_V0"]}
+    assert m.rebuild("keep", unit_types=["CONTENT_TXT_V0"], simprint_types=["CONTENT_TXT_V0"]) == {"unit_types": [], "simprint_types": []}
+    assert (m.search_assets("keep", q_units), m.search_assets("keep", q_sp)) == before
+    m.close()
+
+    # a lost snapshot is rebuilt from the asset log on open
+    import shutil
+
+    shutil.rmtree(tmp_path / "keep" / "DATA_NONE_V0")
+    shutil.rmtree(tmp_path / "keep" / "SIMPRINT_CONTENT_TEXT_V0")
+    m = B200IndexManager(tmp_path)
+    assert (m.search_assets("keep", q_units), m.search_assets("keep", q_sp)) == before
+    m.close()

@@ -37,6 +37,7 @@ def test_product_never_imports_the_oracle():
     for py in (ROOT / "iscc_search_b200").rglob("*.py"):
         src = py.read_text()
         assert "import oracle" not in src and "from oracle" not in src, py
+        assert "import tests" not in src and "from tests" not in src, py  # the oracle-backed store double is test-only
     for src in (ROOT / "iscc_search_b200" / "csrc").iterdir():
         if src.suffix in (".cu", ".cuh", ".hpp"):
             assert "oracle" not in src.read_text().lower(), src
@@ -49,13 +50,18 @@ def _device_count():
 
 
 @pytest.mark.skipif(_device_count() > 0, reason="a GPU is present; this checks the no-device behaviour")
-def test_open_without_device_fails_loudly_no_cpu_fallback():
+def test_open_without_device_fails_loudly_no_cpu_fallback(tmp_path):
     with pytest.raises(_lib.IsxError, match="no CPU fallback"):
         _lib.Store()
     from iscc_search_b200 import ShardedNphdIndex
 
     with pytest.raises(_lib.IsxError):
         ShardedNphdIndex(max_dim=256)
+    from iscc_search_b200.backend import B200IndexManager
+    from iscc_search_b200.schema import IsccIndex
+
+    with pytest.raises(_lib.IsxError, match="no CPU fallback"):  # the protocol backend has no CPU path either
+        B200IndexManager(tmp_path).create_index(IsccIndex(name="nogpu"))
 
 
 def test_argument_validation_happens_before_any_device_work():

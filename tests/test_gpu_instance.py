@@ -49,5 +49,7 @@ def test_instance_bidirectional_prefix_matches_reference_rules(cuda):
     assert idx.search(full[:8]) == {1: 1.0, 2: 1.0, 3: 1.0, 5: 1.0}       # 64-bit query: everything starting with it
     assert idx.search(other[:8]) == {4: 1.0}
     assert idx.search(bytes(8)) == {}
-    assert idx.remove_asset(1) == 2 and idx.search(full) == {2: 1.0, 3: 1.0}
+    assert idx.remove_many([(1, full), (1, full[:8]), (1, other)]) == 2 and idx.search(full) == {2: 1.0, 3: 1.0}
+    idx.add_many([(7, full[:8]), (7, other[:8]), (7, full[:8])])   # same length, two bodies; the repeated pair is skipped
+    assert len(idx) == 6 and idx.search(other) == {4: 1.0, 7: 1.0} and list(idx.search(full[:8])) == [2, 3, 5, 7]
     idx.close()

@@ -1,0 +1,26 @@
+"""IsccIndexProtocol backend on the real HBM stores: reference-generated flow + protocol cases (needs a B200)."""
+
+import pytest
+
+from tests import protocol_cases
+from tests.protocol_replay import replay
+
+pytestmark = pytest.mark.gpu
+
+
+def test_backend_matches_reference_flow_on_gpu(tmp_path, cuda):
+
+    counts = replay(tmp_path)
+    assert counts["search_assets"] > 100
+
+
+def test_index_lifecycle_gpu(tmp_path, cuda):
+    protocol_cases.case_index_lifecycle(tmp_path)
+
+
+def test_add_get_search_gpu(tmp_path, cuda):
+    protocol_cases.case_add_get_search(tmp_path)
+
+
+def test_persistence_and_rebuild_gpu(tmp_path, cuda):
+    protocol_cases.case_persistence_and_rebuild(tmp_path)

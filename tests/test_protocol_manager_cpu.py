@@ -1,0 +1,15 @@
+"""IsccIndexProtocol cases on the oracle-backed store double: host logic of the backend without a GPU."""
+
+from tests import protocol_cases
+
+
+def test_index_lifecycle(tmp_path, cpu_stores):
+    protocol_cases.case_index_lifecycle(tmp_path)
+
+
+def test_add_get_search(tmp_path, cpu_stores):
+    protocol_cases.case_add_get_search(tmp_path)
+
+
+def test_persistence_and_rebuild(tmp_path, cpu_stores):
+    protocol_cases.case_persistence_and_rebuild(tmp_path)
