@@ -6,7 +6,7 @@ bench.py - exact NPHD top-k over 100M mixed-length ISCC-UNITs (BASELINE.json con
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU exact path (restated, oracle/)
 
 Workload (config.workload = "cfg3"): 100M synthetic codes, 25 % each of 64/128/192/256 bit, uint64 keys;
-one step = one batch of Q mixed-length queries (default 1024) answered exactly, k = 100. With N GPUs the
+one step = one batch of Q mixed-length queries (default 10 000, the batch BASELINE.json's configs 2 and 3 name) answered exactly, k = 100. With N GPUs the
 100M rows are row-sharded (strong scaling), every rank scans its shard, the per-rank top-k records are
 all-gathered over NCCL and merged on the device.
 
@@ -44,11 +44,11 @@ HBM_FALLBACK_GBS = 6650.0    # /opt/skills/guides/B200_PROFILING.md fallback whe
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=100_000_000)
-    ap.add_argument("--queries", type=int, default=1024)
+    ap.add_argument("--queries", type=int, default=10_000)
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline leg")
