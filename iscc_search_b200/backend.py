@@ -38,6 +38,9 @@ DEFAULT_OPTIONS = {
     "confidence_exponent": 4,
     "oversampling_factor": 20,
     "flush_interval": 100000,
+    # extension: > 0 routes the unit searches of concurrent `search_assets` calls (the REST server's thread pool,
+    # server/search.py) through one `BatchingFrontDoor` per unit type, so they share GPU batches; 0 = one search per unit
+    "coalesce_ms": 0.0,
 }
 
 SP_FINGERPRINT_BYTES = 16
@@ -99,6 +102,7 @@ class B200Index:
         self._nphd_indexes = {}      # unit_type -> ShardedNphdIndex
         self._simprint_indexes = {}  # sp_type -> B200SimprintIndex
         self._instance = self._stores.instance()
+        self._doors = {}             # unit_type -> BatchingFrontDoor (only with coalesce_ms > 0)
         self._write_lock = threading.RLock()
         self._closed = False
         self._load_derived()
@@ -446,8 +450,11 @@ class B200Index:
         if nphd_index.size == 0:
             return [{} for _ in bodies]
         count = min(int(limit), getattr(nphd_index, "max_count", int(limit)))  # REST `limit` is unbounded above (server/search.py:22)
-        res = nphd_index.search([np.frombuffer(b, dtype=np.uint8) for b in bodies], count=count)
-        per_query = [res] if len(bodies) == 1 else [res[i] for i in range(len(bodies))]
+        if len(bodies) == 1 and self._opts["coalesce_ms"] > 0:
+            per_query = [self._door(unit_type, nphd_index).search(np.frombuffer(bodies[0], dtype=np.uint8), count=count)]
+        else:
+            res = nphd_index.search([np.frombuffer(b, dtype=np.uint8) for b in bodies], count=count)
+            per_query = [res] if len(bodies) == 1 else [res[i] for i in range(len(bodies))]
         out = []
         for m in per_query:
             scores = {}
@@ -455,6 +462,19 @@ class B200Index:
                 scores[int(key)] = max(0.0, 1.0 - float(distance))
             out.append(scores)
         return out
+
+    def _door(self, unit_type, nphd_index):
+        door = self._doors.get(unit_type)
+        if door is None or door.index is not nphd_index:
+            with self._write_lock:
+                door = self._doors.get(unit_type)
+                if door is None or door.index is not nphd_index:
+                    from iscc_search_b200.frontdoor import BatchingFrontDoor
+
+                    if door is not None:
+                        door.close()
+                    door = self._doors[unit_type] = BatchingFrontDoor(nphd_index, max_delay_ms=self._opts["coalesce_ms"])
+        return door
 
     def _search_instance_unit(self, instance_code):
         return self._instance.search(instance_code)
@@ -527,6 +547,9 @@ class B200Index:
         with self._write_lock:
             if self._closed:
                 return
+            for door in self._doors.values():
+                door.close()
+            self._doors.clear()
             for index in list(self._nphd_indexes.values()) + list(self._simprint_indexes.values()):
                 try:
                     if index.dirty:

@@ -167,3 +167,33 @@ def case_persistence_and_rebuild(tmp_path):
     m = B200IndexManager(tmp_path)
     assert (m.search_assets("keep", q_units), m.search_assets("keep", q_sp)) == before
     m.close()
+
+
+def case_concurrent_requests_share_batches(tmp_path):
+    """REST-style concurrency: many threads call search_assets at once; with coalesce_ms > 0 they ride shared GPU batches."""
+    import threading
+
+    m = B200IndexManager(tmp_path, coalesce_ms=20.0)
+    m.create_index(IsccIndex(name="busy"))
+    base = [rnd(300 + i, 16) for i in range(24)]
+    m.add_assets("busy", [IsccEntry(iscc_id=iscc_id(500 + i), units=[unit(ic.MT.DATA, 0, b), unit(ic.MT.INSTANCE, 0, rnd(400 + i, 8))])
+                          for i, b in enumerate(base)])
+    queries = [IsccQuery(units=[unit(ic.MT.DATA, 0, flip(b, [i % 100]))]) for i, b in enumerate(base)]
+    out = {}
+
+    def worker(i):
+        out[i] = m.search_assets("busy", queries[i], limit=5)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(queries))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    door = m._get_or_load_index("busy")._doors["DATA_NONE_V0"]
+    assert door.requests == len(queries) and door.batches < len(queries)
+    m.close()
+    plain = B200IndexManager(tmp_path)   # same index, one search per request
+    for i, q in enumerate(queries):
+        assert out[i] == plain.search_assets("busy", q, limit=5)
+        assert out[i].global_matches[0].iscc_id == iscc_id(500 + i)
+    plain.close()

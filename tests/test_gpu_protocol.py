@@ -24,3 +24,7 @@ def test_add_get_search_gpu(tmp_path, cuda):
 
 def test_persistence_and_rebuild_gpu(tmp_path, cuda):
     protocol_cases.case_persistence_and_rebuild(tmp_path)
+
+
+def test_concurrent_requests_share_batches_gpu(tmp_path, cuda):
+    protocol_cases.case_concurrent_requests_share_batches(tmp_path)

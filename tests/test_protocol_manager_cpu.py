@@ -13,3 +13,7 @@ def test_add_get_search(tmp_path, cpu_stores):
 
 def test_persistence_and_rebuild(tmp_path, cpu_stores):
     protocol_cases.case_persistence_and_rebuild(tmp_path)
+
+
+def test_concurrent_requests_share_batches(tmp_path, cpu_stores):
+    protocol_cases.case_concurrent_requests_share_batches(tmp_path)
