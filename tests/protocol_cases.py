@@ -197,3 +197,66 @@ def case_concurrent_requests_share_batches(tmp_path):
         assert out[i] == plain.search_assets("busy", q, limit=5)
         assert out[i].global_matches[0].iscc_id == iscc_id(500 + i)
     plain.close()
+
+
+def case_reference_index_behaviours(tmp_path):
+    """
+    Behaviours the reference's own index tests pin (tests/test_indexes_usearch_index.py:141-215, 803-826, 948-981,
+    984-1006, 1009-1035), restated against B200Index.
+    """
+    from iscc_search_b200.backend import B200Index
+    from iscc_search_b200.iscc import IsccID
+
+    idx = B200Index(tmp_path / "behaviours", realm_id=0, max_dim=256)
+    # -- INSTANCE matches score 1.0 in both prefix directions (:141-215)
+    base = bytes(range(1, 33))
+    inst = {n: unit(ic.MT.INSTANCE, 0, base[: n // 8]) for n in (64, 128, 256)}
+    content = unit(ic.MT.CONTENT, ic.ST_CC.TEXT, rnd(900, 8))
+    ids = [iscc_id(700 + i) for i in range(6)]
+    idx.add_assets([IsccEntry(iscc_id=ids[i], units=[inst[n], content]) for i, n in enumerate((64, 128, 256))])
+    for n in (64, 128, 256):
+        res = idx.search_assets(IsccQuery(units=[inst[n], content]), limit=10)
+        assert {m.iscc_id for m in res.global_matches} == set(ids[:3])
+        assert all(m.types["INSTANCE_NONE_V0"] == 1.0 and m.types["CONTENT_TEXT_V0"] == 1.0 and m.score == 1.0 for m in res.global_matches)
+    idx.close()
+
+    # -- matches below match_threshold_units are dropped (:803-826)
+    strict = B200Index(tmp_path / "strict", realm_id=0, max_dim=256, match_threshold_units=0.99)
+    body = rnd(901, 8)
+    strict.add_assets([IsccEntry(iscc_id=ids[0], units=[unit(ic.MT.INSTANCE, 0, rnd(902, 16)), unit(ic.MT.CONTENT, ic.ST_CC.TEXT, body)],
+                                 metadata={"name": "Test Asset"})])
+    assert strict.search_assets(IsccQuery(units=[unit(ic.MT.CONTENT, ic.ST_CC.TEXT, flip(body, [5]))]), limit=10).global_matches == []  # 63/64 < 0.99
+    assert len(strict.search_assets(IsccQuery(units=[unit(ic.MT.CONTENT, ic.ST_CC.TEXT, body)]), limit=10).global_matches) == 1
+    strict.close()
+
+    # -- identical re-add: "updated" but no vector mutation; a changed asset re-indexes (:948-981)
+    idx = B200Index(tmp_path / "readd", realm_id=0, max_dim=256)
+    c256 = unit(ic.MT.CONTENT, ic.ST_CC.TEXT, rnd(903, 32))
+    i128 = unit(ic.MT.INSTANCE, 0, rnd(904, 16))
+    asset = IsccEntry(iscc_id=ids[0], units=[i128, c256])
+    assert idx.add_assets([asset])[0].status == Status.created
+    nphd = idx._nphd_indexes["CONTENT_TEXT_V0"]
+    dirty_before = nphd.dirty
+    assert idx.add_assets([asset])[0].status == Status.updated and nphd.dirty == dirty_before
+    changed = IsccEntry(iscc_id=ids[0], units=[i128, c256], metadata={"title": "changed"})
+    assert idx.add_assets([changed])[0].status == Status.updated and nphd.dirty > dirty_before
+    top = idx.search_assets(IsccQuery(units=[c256])).global_matches[0]
+    assert top.iscc_id == ids[0] and top.score == 1.0
+
+    # -- an unchanged re-add re-indexes when the derived vector went missing (:984-1006)
+    nphd.remove([int(IsccID(ids[0]))])
+    assert idx.search_assets(IsccQuery(units=[c256])).global_matches == []
+    assert idx.add_assets([changed])[0].status == Status.updated
+    top = idx.search_assets(IsccQuery(units=[c256])).global_matches[0]
+    assert top.iscc_id == ids[0] and top.score == 1.0
+
+    # -- an update drops INSTANCE bodies the asset no longer carries (:1009-1035)
+    datahash = bytes(range(32))
+    c = rnd(905, 32)
+    idx.add_assets([IsccEntry(iscc_id=ids[1], units=[unit(ic.MT.CONTENT, ic.ST_CC.TEXT, c[:8]), unit(ic.MT.INSTANCE, 0, datahash[:8])])])
+    idx.add_assets([IsccEntry(iscc_id=ids[1], units=[unit(ic.MT.CONTENT, ic.ST_CC.TEXT, c), unit(ic.MT.INSTANCE, 0, datahash)])])
+    foreign = datahash[:8] + bytes(24)
+    assert idx.search_assets(IsccQuery(units=[unit(ic.MT.INSTANCE, 0, foreign)])).global_matches == []
+    top = idx.search_assets(IsccQuery(units=[unit(ic.MT.INSTANCE, 0, datahash)])).global_matches[0]
+    assert top.iscc_id == ids[1] and top.score == 1.0
+    idx.close()

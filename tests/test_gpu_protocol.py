@@ -28,3 +28,7 @@ def test_persistence_and_rebuild_gpu(tmp_path, cuda):
 
 def test_concurrent_requests_share_batches_gpu(tmp_path, cuda):
     protocol_cases.case_concurrent_requests_share_batches(tmp_path)
+
+
+def test_reference_index_behaviours_gpu(tmp_path, cuda):
+    protocol_cases.case_reference_index_behaviours(tmp_path)

@@ -17,3 +17,7 @@ def test_persistence_and_rebuild(tmp_path, cpu_stores):
 
 def test_concurrent_requests_share_batches(tmp_path, cpu_stores):
     protocol_cases.case_concurrent_requests_share_batches(tmp_path)
+
+
+def test_reference_index_behaviours(tmp_path, cpu_stores):
+    protocol_cases.case_reference_index_behaviours(tmp_path)
