@@ -55,11 +55,16 @@ class GpuStores:
     """Factory of the HBM-resident stores of one index (the only product implementation: no CPU variant)."""
 
     def __init__(self, device=0):
-        self.device = device
+        # `device` may be one GPU or a list of GPUs: with several, the unit stores (the exact NPHD top-k path) are
+        # row-sharded over them inside this process; simprint and INSTANCE stores live on the first one
+        self.devices = tuple(device) if isinstance(device, (list, tuple)) else (int(device),)
+        self.device = self.devices[0]
 
     def nphd(self, max_dim, path):
-        from iscc_search_b200.nphd import ShardedNphdIndex
+        from iscc_search_b200.nphd import MultiDeviceNphdIndex, ShardedNphdIndex
 
+        if len(self.devices) > 1:
+            return MultiDeviceNphdIndex(max_dim=max_dim, path=path, devices=self.devices)
         return ShardedNphdIndex(max_dim=max_dim, path=path, device=self.device)
 
     def simprint(self, path, ndim, oversampling_factor):

@@ -337,3 +337,146 @@ class ShardedIndex128(_IndexBase):
                            visited_members=n_rows, computed_distances=n_rows)
         return BatchMatches(keys=keys, distances=dist, counts=counts.astype(np.int64), hamming=h, nbits=nb, vectors=vec, first=first,
                             visited_members=n_rows * len(qlens), computed_distances=n_rows * len(qlens))
+
+
+class MultiDeviceNphdIndex:
+    """
+    `ShardedNphdIndex` row-sharded over several GPUs of ONE process.
+
+    iscc-search serves from a single process (cli/serve.py:43-50, manager.py:43-46), so the protocol backend reaches all
+    GPUs of the box through one store handle per device: a key lives on the device `splitmix64(key) % G` selects
+    (`sharded.owner_of`), every device answers its own exact top-`count` concurrently (one host thread per device; the
+    C ABI releases the GIL) and the G sorted lists are merged on the host under the store's total order - exact rational
+    h/n, then key - so the result is identical to a single-device index. For one process per GPU with an NCCL
+    all-gather and a device merge see `sharded.ShardedSearcher`.
+    """
+
+    def __init__(self, max_dim=256, path=None, devices=(0,), **kw):
+        from concurrent.futures import ThreadPoolExecutor
+
+        if not devices:
+            raise ValueError("devices must name at least one GPU")
+        self.max_dim = max_dim
+        self.path = Path(path) if path is not None else None
+        self.devices = tuple(int(d) for d in devices)
+        self.shards = [ShardedNphdIndex(max_dim=max_dim, path=None if self.path is None else self.path / f"shard{i}", device=d, **kw)
+                       for i, d in enumerate(self.devices)]
+        self._pool = ThreadPoolExecutor(max_workers=len(self.shards), thread_name_prefix="isx-dev")
+
+    def _owner(self, keys):
+        from iscc_search_b200.sharded import owner_of
+
+        return owner_of(keys, len(self.shards))
+
+    def _map(self, fn):
+        return list(self._pool.map(fn, self.shards))
+
+    # -- mutation: every key has exactly one home shard; a key present anywhere is a duplicate (first wins)
+    def add(self, keys, vectors):
+        k, _ = _as_u64_keys(keys)
+        codes, lens = _pack_vectors(vectors, len(k), 0, self.max_dim // 8)
+        if len(k) == 0:
+            return k
+        owner = self._owner(k)
+        for g, shard in enumerate(self.shards):
+            sel = np.nonzero(owner == g)[0]
+            if len(sel):
+                shard.add(k[sel], [codes[i, : lens[i]] for i in sel])
+        return k
+
+    def remove(self, keys):
+        k, _ = _as_u64_keys(keys)
+        if len(k) == 0:
+            return 0
+        owner = self._owner(k)
+        return sum(shard.remove(k[owner == g]) for g, shard in enumerate(self.shards) if np.any(owner == g))
+
+    def contains(self, keys):
+        k, scalar = _as_u64_keys(keys)
+        if len(k) == 0:
+            return np.zeros(0, dtype=bool)
+        owner = self._owner(k)
+        res = np.zeros(len(k), dtype=bool)
+        for g, shard in enumerate(self.shards):
+            sel = np.nonzero(owner == g)[0]
+            if len(sel):
+                res[sel] = shard.contains(k[sel])
+        return bool(res[0]) if scalar else res
+
+    def __contains__(self, key):
+        return bool(self.contains(int(key)))
+
+    def get(self, keys):
+        k, scalar = _as_u64_keys(keys)
+        owner = self._owner(k) if len(k) else []
+        out = [self.shards[int(g)].get(int(key)) for key, g in zip(k, owner)]
+        return out[0] if scalar else out
+
+    # -- search: all shards concurrently, host merge under (h/n, key)
+    def search(self, vectors, count=10, exact=True, **_ignored):
+        if count < 1:
+            raise ValueError("`count` must be >= 1")
+        queries, qlens = _pack_vectors(vectors, None, 0, self.max_dim // 8)
+        q = len(qlens)
+        qlist = [queries[i, : qlens[i]] for i in range(q)]
+        parts = self._map(lambda shard: shard.search(qlist, count=count) if shard.size else None)
+        parts = [p for p in parts if p is not None]
+        n_rows = self.size
+        merged = []
+        for i in range(q):
+            per = [p if q == 1 else p[i] for p in parts]
+            keys = np.concatenate([m.keys for m in per]) if per else np.zeros(0, dtype=np.uint64)
+            h = np.concatenate([m.hamming for m in per]).astype(np.int64) if per else np.zeros(0, dtype=np.int64)
+            nb = np.concatenate([m.nbits for m in per]).astype(np.int64) if per else np.zeros(0, dtype=np.int64)
+            if len(keys):
+                lcm = int(np.lcm.reduce(np.unique(nb)))
+                order = np.lexsort((keys, h * (lcm // nb)))[:count]  # exact: h/n ascending as integers over a common denominator
+            else:
+                order = np.zeros(0, dtype=np.int64)
+            merged.append((keys[order], h[order].astype(np.uint16), nb[order].astype(np.uint16)))
+        if q == 1:
+            keys, h, nb = merged[0]
+            return Matches(keys=keys, distances=(h.astype(np.float32) / np.maximum(nb, 1).astype(np.float32)).astype(np.float32),
+                           hamming=h, nbits=nb, visited_members=n_rows, computed_distances=n_rows)
+        kk = max(1, max(len(m[0]) for m in merged))
+        keys = np.zeros((q, kk), dtype=np.uint64)
+        h = np.zeros((q, kk), dtype=np.uint16)
+        nb = np.zeros((q, kk), dtype=np.uint16)
+        counts = np.zeros(q, dtype=np.int64)
+        for i, (mk, mh, mn) in enumerate(merged):
+            c = len(mk)
+            keys[i, :c], h[i, :c], nb[i, :c], counts[i] = mk, mh, mn, c
+        dist = (h.astype(np.float32) / np.maximum(nb, 1).astype(np.float32)).astype(np.float32)
+        return BatchMatches(keys=keys, distances=dist, counts=counts, hamming=h, nbits=nb,
+                            visited_members=n_rows * q, computed_distances=n_rows * q)
+
+    # -- bookkeeping: sums / fan-out over the shards
+    size = property(lambda self: sum(s.size for s in self.shards))
+    dirty = property(lambda self: sum(s.dirty for s in self.shards))
+    shard_count = property(lambda self: sum(s.shard_count for s in self.shards))
+    serialized_length = property(lambda self: sum(s.serialized_length for s in self.shards))
+    memory_usage = property(lambda self: sum(s.memory_usage for s in self.shards))
+    max_count = property(lambda self: min(s.max_count for s in self.shards))
+    _active_shard_path = property(lambda self: None)
+
+    def __len__(self):
+        return self.size
+
+    def save(self):
+        for s in self.shards:
+            s.save()
+
+    def drain_rotations(self):
+        pass
+
+    def reset(self):
+        for s in self.shards:
+            s.reset()
+
+    def close(self):
+        for s in self.shards:
+            s.close()
+        self._pool.shutdown(wait=True)
+
+    def stats(self):
+        return [s.stats() for s in self.shards]

@@ -260,3 +260,57 @@ def case_reference_index_behaviours(tmp_path):
     top = idx.search_assets(IsccQuery(units=[unit(ic.MT.INSTANCE, 0, datahash)])).global_matches[0]
     assert top.iscc_id == ids[1] and top.score == 1.0
     idx.close()
+
+
+def case_multi_device_equals_single(tmp_path, devices):
+    """Unit stores row-sharded over several devices of one process answer exactly like a single store (order included)."""
+    from iscc_search_b200.nphd import MultiDeviceNphdIndex, ShardedNphdIndex
+
+    rng = np.random.default_rng(77)
+    n = 3000
+    lens = rng.choice([8, 16, 24, 32], size=n)
+    base = [rnd(1000 + i, 32) for i in range(20)]
+    vecs = [flip(base[i % 20], rng.choice(256, size=int(rng.integers(0, 40)), replace=False))[: lens[i]] for i in range(n)]
+    keys = rng.permutation(np.arange(1, n + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15))
+    single = ShardedNphdIndex(max_dim=256)
+    multi = MultiDeviceNphdIndex(max_dim=256, path=tmp_path / "multi", devices=devices)
+    single.add(keys, vecs)
+    multi.add(keys, vecs)
+    multi.add(keys[:10], vecs[:10])  # duplicates are skipped
+    assert multi.size == single.size == n and all(s.size > 0 for s in multi.shards)
+    queries = [base[i % 20][: [8, 16, 24, 32][i % 4]] for i in range(24)]
+    for count in (1, 10, 300):
+        a, b = single.search(queries, count=count), multi.search(queries, count=count)
+        assert np.array_equal(a.counts, b.counts)
+        for i in range(len(queries)):
+            c = int(a.counts[i])
+            assert np.array_equal(a.keys[i, :c], b.keys[i, :c]) and np.array_equal(a.hamming[i, :c], b.hamming[i, :c])
+            assert np.array_equal(a.nbits[i, :c], b.nbits[i, :c]) and np.array_equal(a.distances[i, :c], b.distances[i, :c])
+    one_a, one_b = single.search(queries[3], count=7), multi.search(queries[3], count=7)
+    assert np.array_equal(one_a.keys, one_b.keys) and np.array_equal(one_a.distances, one_b.distances)
+    gone = keys[100:140]
+    assert multi.remove(gone) == single.remove(gone) == 40 and multi.size == n - 40
+    assert not multi.contains(gone).any() and multi.contains(keys[:5]).all() and int(keys[0]) in multi
+    assert np.array_equal(multi.get(int(keys[7])), single.get(int(keys[7]))) and multi.get(int(gone[0])) is None
+    multi.save()
+    multi.close()
+    again = MultiDeviceNphdIndex(max_dim=256, path=tmp_path / "multi", devices=devices)  # snapshots per shard
+    b = again.search(queries, count=10)
+    a = single.search(queries, count=10)
+    assert np.array_equal(a.keys, b.keys) and np.array_equal(a.hamming, b.hamming)
+    again.close()
+    single.close()
+
+    # the protocol backend over several devices: same answers as over one
+    m1 = B200IndexManager(tmp_path / "one")
+    mg = B200IndexManager(tmp_path / "many", device=list(devices))
+    entries_ = [IsccEntry(iscc_id=iscc_id(2000 + i), units=[unit(ic.MT.DATA, 0, vecs[i]), unit(ic.MT.INSTANCE, 0, rnd(3000 + i, 8))])
+                for i in range(200)]
+    for m in (m1, mg):
+        m.create_index(IsccIndex(name="x"))
+        m.add_assets("x", entries_)
+    for qv in queries[:8]:
+        q = IsccQuery(units=[unit(ic.MT.DATA, 0, qv)])
+        assert m1.search_assets("x", q, limit=20) == mg.search_assets("x", q, limit=20)
+    m1.close()
+    mg.close()

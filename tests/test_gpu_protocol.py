@@ -32,3 +32,14 @@ def test_concurrent_requests_share_batches_gpu(tmp_path, cuda):
 
 def test_reference_index_behaviours_gpu(tmp_path, cuda):
     protocol_cases.case_reference_index_behaviours(tmp_path)
+
+
+def test_multi_device_equals_single_gpu(tmp_path, cuda):
+    import ctypes
+
+    from iscc_search_b200 import _lib
+
+    n = ctypes.c_int()
+    _lib.check(_lib.lib().isx_device_count(ctypes.byref(n)))
+    devices = tuple(range(min(n.value, 4))) if n.value > 1 else (0, 0)  # one GPU: two stores on the same device
+    protocol_cases.case_multi_device_equals_single(tmp_path, devices=devices)

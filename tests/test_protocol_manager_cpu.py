@@ -21,3 +21,7 @@ def test_concurrent_requests_share_batches(tmp_path, cpu_stores):
 
 def test_reference_index_behaviours(tmp_path, cpu_stores):
     protocol_cases.case_reference_index_behaviours(tmp_path)
+
+
+def test_multi_device_equals_single(tmp_path, cpu_stores):
+    protocol_cases.case_multi_device_equals_single(tmp_path, devices=(0, 1, 2))
