@@ -306,8 +306,10 @@ static int launch_scan_t(isx_store* s, const ScanParams& p, uint32_t grid_cap_pe
     }
     uint32_t n_blocks = p.block_end - p.block_begin;
     uint32_t n_groups = (n_blocks + G - 1) / G;
-    uint32_t gx = std::min<uint32_t>(n_groups, (uint32_t)s->sm_count * grid_cap_per_sm);
-    if (gx == 0) return 0;
+    if (n_groups == 0) return 0;
+    const uint32_t cap = (uint32_t)s->sm_count * grid_cap_per_sm;
+    const uint32_t per = (n_groups + cap - 1) / cap;   // groups per CTA
+    const uint32_t gx = (n_groups + per - 1) / per;    // equal shares (they differ by at most one group)
     dim3 grid(gx, (p.T + p.q_split - 1) / p.q_split, 1);
     k_scan<WE, G, MINB><<<grid, kThreads, smem, stream>>>(p);
     CU(cudaGetLastError());
@@ -323,10 +325,11 @@ static int launch_scan(isx_store* s, ScanParams& p, uint32_t we, uint32_t bpi_hi
     p.blocks_per_item = std::max(G, (bpi_hint / G) * G);
     const uint32_t per_sm = 3;  // resident CTAs per SM (register bound, __launch_bounds__(256, 3); 4 CTAs of 64
                                 // registers measured no faster - the POPC pipe, not occupancy, is the limit)
-    // small ranges: split the query tile over gridDim.y so ~2 waves of CTAs exist
+    // small ranges: split the query tile over gridDim.y so ~8 waves of CTAs exist. Finer work units cut the tail of a launch
+    // whose CTAs all take equally long (measured on a 12.5 M-row shard, 8192 queries: 2 waves 81.7 ms, 4 waves 80.4, 8 waves 78.4)
     {
         uint32_t n_items = (p.block_end - p.block_begin + G - 1) / G;
-        uint32_t want = (uint32_t)s->sm_count * per_sm * 2;
+        uint32_t want = (uint32_t)s->sm_count * per_sm * 8;
         uint32_t splits = n_items >= want ? 1 : std::min<uint32_t>(p.T, (want + n_items - 1) / n_items);
         p.q_split = (p.T + splits - 1) / splits;
     }

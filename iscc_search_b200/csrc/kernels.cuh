@@ -252,9 +252,11 @@ __global__ void __launch_bounds__(kThreads, MINB) k_scan(const __grid_constant__
     for (uint32_t i = tid; i < p.R; i += kThreads) s_hrow[i] = p.hmax_tab[(size_t)m * p.R + i];
     __syncthreads();
 
-    const uint64_t n_blocks = p.block_end - p.block_begin;
-    const uint32_t my_lo = p.block_begin + (uint32_t)(n_blocks * blockIdx.x / gridDim.x);
-    const uint32_t my_hi = p.block_begin + (uint32_t)(n_blocks * (blockIdx.x + 1) / gridDim.x);
+    // shares are whole groups of G blocks, so only the launch's very last group can be partial (a partial group costs a
+    // full pass over the query tile: with 6-7 blocks per CTA on a small shard that was 14-25 % of the work)
+    const uint64_t n_groups = ((uint64_t)(p.block_end - p.block_begin) + G - 1) / G;
+    const uint32_t my_lo = p.block_begin + G * (uint32_t)(n_groups * blockIdx.x / gridDim.x);
+    const uint32_t my_hi = min(p.block_end, p.block_begin + G * (uint32_t)(n_groups * (blockIdx.x + 1) / gridDim.x));
     // small tiles (one query per thread at most): the next item's bound is fetched while this item streams
     const bool prefetch = (T <= kThreads);
     uint32_t hm_next = 0;

@@ -10,7 +10,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def child(lib_path, rows, queries, k, reps):
+def child(lib_path, rows, queries, k, reps, mixed_only=False):
     sys.path.insert(0, str(ROOT))
     import numpy as np
 
@@ -18,7 +18,7 @@ def child(lib_path, rows, queries, k, reps):
 
     _lib.SO_PATH = Path(lib_path).resolve()
     out = []
-    for L in (8, 16, 24, 32):
+    for L in (() if mixed_only else (8, 16, 24, 32)):
         st = _lib.Store(key_bytes=8, max_bytes=32)
         st.set_profiling(True)
         for c0 in range(0, rows, 2_000_000):
@@ -56,10 +56,11 @@ if __name__ == "__main__":
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--child", action="store_true")
+    ap.add_argument("--mixed-only", action="store_true", help="only the mixed-length store (2 x rows)")
     a = ap.parse_args()
     if a.child:
-        child(a.libs[0], a.rows, a.queries, a.k, a.reps)
+        child(a.libs[0], a.rows, a.queries, a.k, a.reps, a.mixed_only)
     else:
         for lib in a.libs:
             subprocess.run([sys.executable, __file__, lib, "--child", "--rows", str(a.rows), "--queries", str(a.queries),
-                            "--k", str(a.k), "--reps", str(a.reps)], check=False)
+                            "--k", str(a.k), "--reps", str(a.reps)] + (["--mixed-only"] if a.mixed_only else []), check=False)
