@@ -331,6 +331,7 @@ static int launch_scan(isx_store* s, ScanParams& p, uint32_t we, uint32_t bpi_hi
         uint32_t n_items = (p.block_end - p.block_begin + G - 1) / G;
         uint32_t want = (uint32_t)s->sm_count * per_sm * 8;
         uint32_t splits = n_items >= want ? 1 : std::min<uint32_t>(p.T, (want + n_items - 1) / n_items);
+        splits = std::min<uint32_t>(splits, std::max<uint32_t>(1, p.T / 32));  // >= 32 queries per CTA: its set-up (tables, tile) must stay small next to its work
         p.q_split = (p.T + splits - 1) / splits;
     }
     switch (we) {
