@@ -116,6 +116,13 @@ class AssetLog:
         self.stale_records = 0
         self._fh = open(self.path / self.LOG, "ab")
 
+    def log_bytes(self):
+        # type: () -> int
+        """Size of the record log including buffered appends: the version stamp the derived-store snapshots are tied to."""
+        if self._fh is not None:
+            self._fh.flush()
+        return (self.path / self.LOG).stat().st_size
+
     def used_bytes(self):
         # type: () -> int
         self._fh.flush()

@@ -18,6 +18,7 @@ many queries, one GPU batch per unit type, results identical to sequential `sear
 """
 
 import hashlib
+import json
 import shutil
 import struct
 import threading
@@ -127,14 +128,31 @@ class B200Index:
                         rows[key] = unit.body  # keep the longest body per key (index.py:1667-1685)
         return best, instance
 
+    DERIVED_MARKER = "derived.json"
+
+    def _snapshots_current(self):
+        """Snapshots are trusted only if the asset log has not grown since they were written (flush / close)."""
+        marker = self.path / self.DERIVED_MARKER
+        try:
+            return json.loads(marker.read_text())["log_bytes"] == self._log.log_bytes()
+        except (OSError, ValueError, KeyError):
+            return False
+
+    def _mark_snapshots(self):
+        tmp = self.path / (self.DERIVED_MARKER + ".tmp")
+        tmp.write_text(json.dumps({"log_bytes": self._log.log_bytes()}))
+        tmp.replace(self.path / self.DERIVED_MARKER)
+
     def _load_derived(self):
         best, instance = self._unit_rows()
         self._instance.add_many(instance)
+        trusted = self._snapshots_current()
         for unit_type, rows in best.items():
+            if not trusted:
+                shutil.rmtree(self.path / unit_type, ignore_errors=True)
             index = self._stores.nphd(self.max_dim, self.path / unit_type)
-            if index.size != len(rows):  # snapshot missing or out of step with the log: rebuild
+            if index.size != len(rows):  # snapshot missing or out of step with the log: rebuild (index.py:1602-1648)
                 index.reset()
-                index = self._stores.nphd(self.max_dim, self.path / unit_type)
                 index.add(list(rows.keys()), list(rows.values()))
                 index.save()
             self._nphd_indexes[unit_type] = index
@@ -143,13 +161,16 @@ class B200Index:
             if not keys:
                 continue
             sp_dir, ndim = self.path / f"SIMPRINT_{sp_type}", 8 * len(vectors[0])
+            if not trusted:
+                shutil.rmtree(sp_dir, ignore_errors=True)
             index = self._stores.simprint(sp_dir, ndim, self._opts["oversampling_factor"])
             if index.size != len(set(keys)):
                 index.reset()
-                index = self._stores.simprint(sp_dir, ndim, self._opts["oversampling_factor"])
                 index.add_raw(keys, vectors)
                 index.save()
             self._simprint_indexes[sp_type] = index
+        if not trusted and (self._nphd_indexes or self._simprint_indexes):
+            self._mark_snapshots()
 
     @property
     def tracked_unit_types(self):
@@ -545,6 +566,7 @@ class B200Index:
             for index in list(self._nphd_indexes.values()) + list(self._simprint_indexes.values()):
                 if index.dirty:
                     index.save()
+            self._mark_snapshots()
 
     def close(self):
         if self._closed:
@@ -555,17 +577,20 @@ class B200Index:
             for door in self._doors.values():
                 door.close()
             self._doors.clear()
+            all_saved = True
             for index in list(self._nphd_indexes.values()) + list(self._simprint_indexes.values()):
                 try:
                     if index.dirty:
                         index.save()
                     index.close()
                 except Exception:  # pragma: no cover - one failing store must not keep the others from saving
-                    pass
+                    all_saved = False
             self._nphd_indexes.clear()
             self._simprint_indexes.clear()
             self._instance.close()
-            self._log.close()
+            self._log.close()  # may compact the log: the marker is written after it
+            if all_saved:
+                self._mark_snapshots()
             self._closed = True
 
     def __len__(self):

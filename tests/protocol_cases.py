@@ -314,3 +314,35 @@ def case_multi_device_equals_single(tmp_path, devices):
         assert m1.search_assets("x", q, limit=20) == mg.search_assets("x", q, limit=20)
     m1.close()
     mg.close()
+
+
+def case_crash_recovery(tmp_path):
+    """Snapshots of the derived stores are trusted only if the asset log has not grown since they were written."""
+    from iscc_search_b200.backend import B200Index
+
+    path = tmp_path / "crashy"
+    body_a, body_b = rnd(4000, 16), rnd(4001, 16)
+    a = IsccEntry(iscc_id=iscc_id(4000), units=[unit(ic.MT.DATA, 0, body_a), unit(ic.MT.INSTANCE, 0, rnd(4002, 8))])
+    idx = B200Index(path, realm_id=0)
+    idx.add_assets([a])
+    idx.close()                                     # clean shutdown: snapshot + marker
+    idx = B200Index(path)
+    assert idx._snapshots_current()
+    # an update and a new asset, then the process dies without flush/close (same row count for asset a, new vector)
+    a2 = IsccEntry(iscc_id=a.iscc_id, units=[unit(ic.MT.DATA, 0, body_b), unit(ic.MT.INSTANCE, 0, rnd(4002, 8))])
+    b = IsccEntry(iscc_id=iscc_id(4001), units=[unit(ic.MT.DATA, 0, flip(body_b, [1])), unit(ic.MT.INSTANCE, 0, rnd(4003, 8))])
+    idx.add_assets([a2, b])
+    idx._log.commit()                               # the host log reached the disk, the derived snapshots did not
+    for ix in idx._nphd_indexes.values():
+        ix._dirty = 0                               # "crash": nothing gets saved on the way out
+    idx._nphd_indexes.clear()
+    idx._log._fh.close()
+    idx._log._fh = None
+    idx._closed = True
+
+    again = B200Index(path)                         # stale snapshot (old vector of a, b missing) must not be used
+    res = again.search_assets(IsccQuery(units=[unit(ic.MT.DATA, 0, body_b)]), limit=10)
+    assert [(m.iscc_id, m.types["DATA_NONE_V0"]) for m in res.global_matches][:2] == [(a.iscc_id, 1.0), (b.iscc_id, 1.0 - 1 / 128)]
+    assert again.search_assets(IsccQuery(units=[unit(ic.MT.DATA, 0, body_a)]), limit=10).global_matches[0].score < 1.0
+    assert again._snapshots_current()
+    again.close()

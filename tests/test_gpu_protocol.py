@@ -43,3 +43,7 @@ def test_multi_device_equals_single_gpu(tmp_path, cuda):
     _lib.check(_lib.lib().isx_device_count(ctypes.byref(n)))
     devices = tuple(range(min(n.value, 4))) if n.value > 1 else (0, 0)  # one GPU: two stores on the same device
     protocol_cases.case_multi_device_equals_single(tmp_path, devices=devices)
+
+
+def test_crash_recovery_gpu(tmp_path, cuda):
+    protocol_cases.case_crash_recovery(tmp_path)

@@ -25,3 +25,7 @@ def test_reference_index_behaviours(tmp_path, cpu_stores):
 
 def test_multi_device_equals_single(tmp_path, cpu_stores):
     protocol_cases.case_multi_device_equals_single(tmp_path, devices=(0, 1, 2))
+
+
+def test_crash_recovery(tmp_path, cpu_stores):
+    protocol_cases.case_crash_recovery(tmp_path)
