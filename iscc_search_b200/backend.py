@@ -130,46 +130,51 @@ class B200Index:
 
     DERIVED_MARKER = "derived.json"
 
-    def _snapshots_current(self):
-        """Snapshots are trusted only if the asset log has not grown since they were written (flush / close)."""
-        marker = self.path / self.DERIVED_MARKER
+    def _snapshot_sizes(self):
+        """
+        {store directory name: row count} recorded at the last flush / close, or None when the asset log has grown
+        since (the process died before saving): snapshots are trusted only for the log version they were written at.
+        The recorded counts play the role of the reference's `nphd_count:*` / `sp_count:*` metadata (index.py:1536-1549).
+        """
         try:
-            return json.loads(marker.read_text())["log_bytes"] == self._log.log_bytes()
+            marker = json.loads((self.path / self.DERIVED_MARKER).read_text())
+            return marker["sizes"] if marker["log_bytes"] == self._log.log_bytes() else None
         except (OSError, ValueError, KeyError):
-            return False
+            return None
 
     def _mark_snapshots(self):
+        sizes = {t: ix.size for t, ix in self._nphd_indexes.items()}
+        sizes.update({f"SIMPRINT_{t}": ix.size for t, ix in self._simprint_indexes.items()})
         tmp = self.path / (self.DERIVED_MARKER + ".tmp")
-        tmp.write_text(json.dumps({"log_bytes": self._log.log_bytes()}))
+        tmp.write_text(json.dumps({"log_bytes": self._log.log_bytes(), "sizes": sizes}))
         tmp.replace(self.path / self.DERIVED_MARKER)
 
     def _load_derived(self):
         best, instance = self._unit_rows()
         self._instance.add_many(instance)
-        trusted = self._snapshots_current()
+        recorded = self._snapshot_sizes()
+        rebuilt = recorded is None
         for unit_type, rows in best.items():
-            if not trusted:
-                shutil.rmtree(self.path / unit_type, ignore_errors=True)
             index = self._stores.nphd(self.max_dim, self.path / unit_type)
-            if index.size != len(rows):  # snapshot missing or out of step with the log: rebuild (index.py:1602-1648)
+            if recorded is None or index.size != recorded.get(unit_type):  # snapshot missing, stale or truncated: rebuild (index.py:1602-1648)
                 index.reset()
                 index.add(list(rows.keys()), list(rows.values()))
                 index.save()
+                rebuilt = True
             self._nphd_indexes[unit_type] = index
         for sp_type in self._log.simprints:
             keys, vectors = self._simprint_rows(sp_type)
             if not keys:
                 continue
-            sp_dir, ndim = self.path / f"SIMPRINT_{sp_type}", 8 * len(vectors[0])
-            if not trusted:
-                shutil.rmtree(sp_dir, ignore_errors=True)
-            index = self._stores.simprint(sp_dir, ndim, self._opts["oversampling_factor"])
-            if index.size != len(set(keys)):
+            name, ndim = f"SIMPRINT_{sp_type}", 8 * len(vectors[0])
+            index = self._stores.simprint(self.path / name, ndim, self._opts["oversampling_factor"])
+            if recorded is None or index.size != recorded.get(name):
                 index.reset()
                 index.add_raw(keys, vectors)
                 index.save()
+                rebuilt = True
             self._simprint_indexes[sp_type] = index
-        if not trusted and (self._nphd_indexes or self._simprint_indexes):
+        if rebuilt and (self._nphd_indexes or self._simprint_indexes):
             self._mark_snapshots()
 
     @property
@@ -582,15 +587,19 @@ class B200Index:
                 try:
                     if index.dirty:
                         index.save()
-                    index.close()
                 except Exception:  # pragma: no cover - one failing store must not keep the others from saving
                     all_saved = False
-            self._nphd_indexes.clear()
-            self._simprint_indexes.clear()
-            self._instance.close()
             self._log.close()  # may compact the log: the marker is written after it
             if all_saved:
                 self._mark_snapshots()
+            for index in list(self._nphd_indexes.values()) + list(self._simprint_indexes.values()):
+                try:
+                    index.close()
+                except Exception:  # pragma: no cover
+                    pass
+            self._nphd_indexes.clear()
+            self._simprint_indexes.clear()
+            self._instance.close()
             self._closed = True
 
     def __len__(self):
