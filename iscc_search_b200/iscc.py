@@ -238,6 +238,15 @@ def decode_units(unit_id):
     return UNITS[unit_id]
 
 
+def encode_component(mtype, stype, version, bit_length, digest):
+    # type: (int, int, int, int, bytes) -> str
+    """Header + the first `bit_length` bits of `digest` as base32 without the `ISCC:` prefix (aggregator/entry.py:90)."""
+    if mtype in (MT.ISCC, MT.ID):
+        raise ValueError(f"{MT(mtype).name} is not a unit")
+    nbytes = bit_length // 8
+    return encode_base32(encode_header(mtype, stype, version, encode_length(mtype, bit_length)) + bytes(digest[:nbytes]))
+
+
 def gen_iscc_code(codes, wide=False):
     # type: (list[str], bool) -> dict
     """

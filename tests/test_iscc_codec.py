@@ -106,3 +106,17 @@ def test_normalize_query_fills_the_missing_representation():
     assert entries.normalize_query(sp) is sp
     with pytest.raises(ValueError, match="Query must have"):
         entries.normalize_query(IsccQuery())
+
+
+def test_idp_example_code_matches_its_independent_datahash():
+    # tests/conftest.py:295-296 of the reference: an ISCC-CODE and the multihash (0x1e20 = BLAKE3-256) of the same file.
+    # The Instance-Code is the head of that hash, so the last unit of the decomposed code must equal its first 64 bits.
+    code = ic.IsccCode("ISCC:KACWN77F73NA44D6EUG3S3QNJIL2BPPQFMW6ZX6CZNOKPAK23S2IJ2I")
+    datahash = bytes.fromhex("1e205ca7815adcb484e9a136c11efe69c1d530176d549b5d18d038eb5280b4b3470c")
+    units = code.units
+    assert [u.unit_type for u in units] == ["META_NONE_V0", "CONTENT_TEXT_V0", "DATA_NONE_V0", "INSTANCE_NONE_V0"]
+    assert units[-1].body == datahash[2:10]
+    # the 256-bit INSTANCE unit the aggregator builds from the datahash (aggregator/entry.py:90-92) extends that unit
+    full = ic.IsccUnit("ISCC:" + ic.encode_component(ic.MT.INSTANCE, ic.ST.NONE, ic.VS.V0, 256, datahash[2:]))
+    assert full.unit_type == "INSTANCE_NONE_V0" and len(full) == 256 and full.body[:8] == units[-1].body
+    assert ic.gen_iscc_code([str(u) for u in units])["iscc"] == str(code)
