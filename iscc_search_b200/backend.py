@@ -56,8 +56,8 @@ class GpuStores:
     """Factory of the HBM-resident stores of one index (the only product implementation: no CPU variant)."""
 
     def __init__(self, device=0):
-        # `device` may be one GPU or a list of GPUs: with several, the unit stores (the exact NPHD top-k path) are
-        # row-sharded over them inside this process; simprint and INSTANCE stores live on the first one
+        # `device` may be one GPU or a list of GPUs: with several, the unit stores (exact NPHD top-k) and the simprint
+        # stores are row-sharded over them inside this process; the small INSTANCE store lives on the first one
         self.devices = tuple(device) if isinstance(device, (list, tuple)) else (int(device),)
         self.device = self.devices[0]
 
@@ -71,7 +71,8 @@ class GpuStores:
     def simprint(self, path, ndim, oversampling_factor):
         from iscc_search_b200.simprint import B200SimprintIndex
 
-        return B200SimprintIndex(path=path, ndim=ndim, oversampling_factor=oversampling_factor, device=self.device)
+        return B200SimprintIndex(path=path, ndim=ndim, oversampling_factor=oversampling_factor,
+                                 device=self.devices if len(self.devices) > 1 else self.device)
 
     def instance(self):
         from iscc_search_b200.instance import InstancePrefixIndex

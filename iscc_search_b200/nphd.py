@@ -480,3 +480,151 @@ class MultiDeviceNphdIndex:
 
     def stats(self):
         return [s.stats() for s in self.shards]
+
+
+class MultiDeviceIndex128:
+    """
+    `ShardedIndex128` row-sharded over several GPUs of ONE process (see `MultiDeviceNphdIndex`).
+
+    A composite key lives on the device its asset selects (`splitmix64(first 8 key bytes) % G`), so all chunks of an
+    asset share a device and the per-shard "best record of its asset" flags stay valid after the merge. Every device
+    answers its own exact top-`count` (threshold pushed down), the host merges under (Hamming distance, 16-byte key).
+    """
+
+    def __init__(self, ndim=128, metric="hamming", dtype="b1", path=None, devices=(0,), **kw):
+        from concurrent.futures import ThreadPoolExecutor
+
+        if not devices:
+            raise ValueError("devices must name at least one GPU")
+        self.ndim = ndim
+        self.path = Path(path) if path is not None else None
+        self.devices = tuple(int(d) for d in devices)
+        self.shards = [ShardedIndex128(ndim=ndim, metric=metric, dtype=dtype, path=None if self.path is None else self.path / f"shard{i}",
+                                       device=d, **kw) for i, d in enumerate(self.devices)]
+        self._pool = ThreadPoolExecutor(max_workers=len(self.shards), thread_name_prefix="isx-dev")
+
+    _normalize_batch_keys = ShardedIndex128._normalize_batch_keys
+    _raw_keys = ShardedIndex128._raw_keys
+
+    def _owner(self, raw_keys):
+        from iscc_search_b200.sharded import owner_of
+
+        asset = np.ascontiguousarray(raw_keys[:, :8]).view(">u8").ravel().astype(np.uint64)
+        return owner_of(asset, len(self.shards))
+
+    def add(self, keys, vectors):
+        k = self._raw_keys(keys)
+        codes, _lens = _pack_vectors(vectors, len(k), self.ndim // 8, self.ndim // 8)
+        if len(k):
+            owner = self._owner(k)
+            for g, shard in enumerate(self.shards):
+                sel = np.nonzero(owner == g)[0]
+                if len(sel):
+                    shard.add(k[sel], codes[sel, : self.ndim // 8])
+        return self._normalize_batch_keys(keys)
+
+    def remove(self, keys):
+        k = self._raw_keys(keys)
+        if len(k) == 0:
+            return 0
+        owner = self._owner(k)
+        return sum(shard.remove(k[owner == g]) for g, shard in enumerate(self.shards) if np.any(owner == g))
+
+    def contains(self, keys):
+        scalar = isinstance(keys, (bytes, bytearray))
+        k = self._raw_keys(keys)
+        if len(k) == 0:
+            return np.zeros(0, dtype=bool)
+        owner = self._owner(k)
+        res = np.zeros(len(k), dtype=bool)
+        for g, shard in enumerate(self.shards):
+            sel = np.nonzero(owner == g)[0]
+            if len(sel):
+                res[sel] = shard.contains(k[sel])
+        return bool(res[0]) if scalar else res
+
+    def __contains__(self, key):
+        return bool(self.contains(bytes(key)))
+
+    def get(self, keys):
+        scalar = isinstance(keys, (bytes, bytearray))
+        k = self._raw_keys(keys)
+        owner = self._owner(k) if len(k) else []
+        out = [self.shards[int(g)].get(bytes(key)) for key, g in zip(k, owner)]
+        return out[0] if scalar else out
+
+    def search(self, vectors, count=10, exact=True, threshold_bits=None, with_vectors=False, with_first=False, **_ignored):
+        if count < 1:
+            raise ValueError("`count` must be >= 1")
+        queries, qlens = _pack_vectors(vectors, None, self.ndim // 8, self.ndim // 8)
+        q, nbytes = len(qlens), self.ndim // 8
+        batch = np.ascontiguousarray(queries[:, :nbytes])
+        parts = list(self._pool.map(lambda shard: shard.search(batch, count=count, threshold_bits=threshold_bits, with_vectors=with_vectors,
+                                                               with_first=with_first) if shard.size else None, self.shards))
+        parts = [p for p in parts if p is not None]
+        n_rows = self.size
+        merged = []
+        for i in range(q):
+            per = [p if q == 1 else p[i] for p in parts]
+            per = [m for m in per if len(m)]
+            if per:
+                keys = np.concatenate([np.asarray(m.keys, dtype=np.uint8).reshape(-1, 16) for m in per])
+                h = np.concatenate([m.hamming for m in per])
+                hi = np.ascontiguousarray(keys[:, :8]).view(">u8").ravel()
+                lo = np.ascontiguousarray(keys[:, 8:]).view(">u8").ravel()
+                order = np.lexsort((lo, hi, h))[:count]
+                rec = {"keys": keys[order], "h": h[order], "nb": np.concatenate([m.nbits for m in per])[order],
+                       "vec": np.concatenate([m.vectors for m in per])[order] if with_vectors else None,
+                       "first": np.concatenate([m.first for m in per])[order] if with_first else None}
+            else:
+                rec = {"keys": np.zeros((0, 16), dtype=np.uint8), "h": np.zeros(0, dtype=np.uint16), "nb": np.zeros(0, dtype=np.uint16),
+                       "vec": np.zeros((0, nbytes), dtype=np.uint8) if with_vectors else None,
+                       "first": np.zeros(0, dtype=np.uint8) if with_first else None}
+            merged.append(rec)
+        if q == 1:
+            r = merged[0]
+            return Matches(keys=r["keys"], distances=r["h"].astype(np.float32), hamming=r["h"], nbits=r["nb"], vectors=r["vec"],
+                           first=r["first"], visited_members=n_rows, computed_distances=n_rows)
+        kk = max(1, max(len(r["h"]) for r in merged))
+        keys = np.zeros((q, kk, 16), dtype=np.uint8)
+        h = np.zeros((q, kk), dtype=np.uint16)
+        nb = np.zeros((q, kk), dtype=np.uint16)
+        vec = np.zeros((q, kk, nbytes), dtype=np.uint8) if with_vectors else None
+        first = np.zeros((q, kk), dtype=np.uint8) if with_first else None
+        counts = np.zeros(q, dtype=np.int64)
+        for i, r in enumerate(merged):
+            c = len(r["h"])
+            keys[i, :c], h[i, :c], nb[i, :c], counts[i] = r["keys"], r["h"], r["nb"], c
+            if with_vectors:
+                vec[i, :c] = r["vec"]
+            if with_first:
+                first[i, :c] = r["first"]
+        return BatchMatches(keys=keys, distances=h.astype(np.float32), counts=counts, hamming=h, nbits=nb, vectors=vec, first=first,
+                            visited_members=n_rows * q, computed_distances=n_rows * q)
+
+    size = property(lambda self: sum(s.size for s in self.shards))
+    dirty = property(lambda self: sum(s.dirty for s in self.shards))
+    shard_count = property(lambda self: sum(s.shard_count for s in self.shards))
+    serialized_length = property(lambda self: sum(s.serialized_length for s in self.shards))
+    memory_usage = property(lambda self: sum(s.memory_usage for s in self.shards))
+    max_count = property(lambda self: min(s.max_count for s in self.shards))
+    _active_shard_path = property(lambda self: None)
+
+    def __len__(self):
+        return self.size
+
+    def save(self):
+        for s in self.shards:
+            s.save()
+
+    def drain_rotations(self):
+        pass
+
+    def reset(self):
+        for s in self.shards:
+            s.reset()
+
+    def close(self):
+        for s in self.shards:
+            s.close()
+        self._pool.shutdown(wait=True)

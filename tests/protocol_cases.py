@@ -301,10 +301,44 @@ def case_multi_device_equals_single(tmp_path, devices):
     again.close()
     single.close()
 
+    # simprint stores: threshold search with IDF scoring, equality join and document frequencies
+    from iscc_search_b200.simprint import B200SimprintIndex, pack_chunk_pointer
+
+    sp_one = B200SimprintIndex(path=None, ndim=64, oversampling_factor=20)
+    sp_many = B200SimprintIndex(path=tmp_path / "sp_many", ndim=64, oversampling_factor=20, device=tuple(devices))
+    sp_base = [rnd(5000 + i, 8) for i in range(12)]
+    sp_keys, sp_vecs = [], []
+    for a in range(60):
+        body = int(2**40 + a * 7919).to_bytes(8, "big")
+        for c in range(int(rng.integers(1, 6))):
+            v = flip(sp_base[int(rng.integers(0, 12))], rng.choice(64, size=int(rng.choice([0, 0, 1, 3, 9, 16, 20])), replace=False))
+            sp_keys.append(pack_chunk_pointer(body, c * 100, 100))
+            sp_vecs.append(np.frombuffer(v, dtype=np.uint8))
+    for ix in (sp_one, sp_many):
+        ix.add_raw(sp_keys, sp_vecs)
+    assert sp_many.size == sp_one.size == len(sp_keys) and sp_keys[5] in sp_many
+    for limit, threshold in ((5, 0.0), (3, 0.75), (50, 0.9)):
+        for query in (sp_base[:4], sp_base[5:6], [bytes(v) for v in sp_vecs[:3]]):
+            a = sp_one.search_raw(query, limit=limit, threshold=threshold, detailed=True, doc_freq_fn="index", total_assets=60)
+            b = sp_many.search_raw(query, limit=limit, threshold=threshold, detailed=True, doc_freq_fn="index", total_assets=60)
+            assert a == b and (threshold > 0.8 or len(a) > 0)
+            assert sp_one.search_exact(query, total_assets=60, limit=limit, threshold=threshold, detailed=True) == \
+                sp_many.search_exact(query, total_assets=60, limit=limit, threshold=threshold, detailed=True)
+    some = [bytes(v) for v in sp_vecs[:20]]
+    assert sp_one.doc_freqs(some) == sp_many.doc_freqs(some) and sp_one.equal_keys(some, 3) == sp_many.equal_keys(some, 3)
+    sp_many.remove(sp_keys[:7])
+    sp_one.remove(sp_keys[:7])
+    assert sp_many.size == sp_one.size and sp_keys[0] not in sp_many
+    assert sp_one.search_raw(sp_base[:4], limit=5, detailed=True) == sp_many.search_raw(sp_base[:4], limit=5, detailed=True)
+    sp_one.close()
+    sp_many.close()
+
     # the protocol backend over several devices: same answers as over one
     m1 = B200IndexManager(tmp_path / "one")
     mg = B200IndexManager(tmp_path / "many", device=list(devices))
-    entries_ = [IsccEntry(iscc_id=iscc_id(2000 + i), units=[unit(ic.MT.DATA, 0, vecs[i]), unit(ic.MT.INSTANCE, 0, rnd(3000 + i, 8))])
+    entries_ = [IsccEntry(iscc_id=iscc_id(2000 + i), units=[unit(ic.MT.DATA, 0, vecs[i]), unit(ic.MT.INSTANCE, 0, rnd(3000 + i, 8))],
+                          simprints={"CONTENT_TEXT_V0": [{"simprint": ic.encode_base64(bytes(sp_vecs[(3 * i + j) % len(sp_vecs)])), "offset": 10 * j,
+                                                          "size": 10} for j in range(1 + i % 3)]} if i % 2 else None)
                 for i in range(200)]
     for m in (m1, mg):
         m.create_index(IsccIndex(name="x"))
@@ -312,6 +346,11 @@ def case_multi_device_equals_single(tmp_path, devices):
     for qv in queries[:8]:
         q = IsccQuery(units=[unit(ic.MT.DATA, 0, qv)])
         assert m1.search_assets("x", q, limit=20) == mg.search_assets("x", q, limit=20)
+    q = IsccQuery(simprints={"CONTENT_TEXT_V0": [ic.encode_base64(b) for b in sp_base[:5]]})
+    r1, rg = m1.search_assets("x", q, limit=20), mg.search_assets("x", q, limit=20)
+    assert r1 == rg and len(r1.chunk_matches) > 0
+    i1, ig = m1._get_or_load_index("x"), mg._get_or_load_index("x")
+    assert i1.search_assets(q, limit=20, exact=True) == ig.search_assets(q, limit=20, exact=True)
     m1.close()
     mg.close()
 
