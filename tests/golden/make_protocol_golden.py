@@ -486,8 +486,8 @@ def dump_result(res):
     return {"query": d["query"], "global_matches": d.get("global_matches", []), "chunk_matches": d.get("chunk_matches", [])}
 
 
-def run(index_mod, schema, tmp):
-    rng = np.random.default_rng(20261019)
+def run(index_mod, schema, tmp, seed=20261019, n_assets=70):
+    rng = np.random.default_rng(seed)
     MT, ST_CC = codec.MT, codec.ST_CC
     steps = []
 
@@ -498,7 +498,7 @@ def run(index_mod, schema, tmp):
             steps.append({"op": op, "args": args, "error": type(e).__name__, "message": str(e)})
 
     idx = index_mod.UsearchIndex(tmp / "flow", realm_id=None, max_dim=256)
-    assets, fam = make_assets(rng, 70)
+    assets, fam = make_assets(rng, n_assets)
     E = schema.IsccEntry
 
     def add(batch):
@@ -560,6 +560,41 @@ def run(index_mod, schema, tmp):
         mixed = {"units": [unit(MT.DATA, 0, f["data"][:8])], "simprints": {"CONTENT_TEXT_V0": [b64(flip(rng, f["sp64"][1], 2))],
                                                                             "UNKNOWN_TYPE_V0": [b64(rnd(rng, 8)) + "A"]}}
         record("search_assets", {"query": mixed, "limit": 10, "exact": False}, lambda mixed=mixed: search(mixed, 10))
+
+    # ---- second act: less common shapes
+    # an asset that carries one unit type at two lengths (both share the asset's key: the last one is indexed, :420-430),
+    # a query with two units of one type (per-type max, :806), an asset whose update drops a unit type and its simprints
+    two_len = {"iscc_id": codec.gen_iscc_id(timestamp=8_000_001, hub_id=5, realm_id=0)["iscc"],
+               "units": [unit(MT.CONTENT, ST_CC.TEXT, fam[2]["content"][:8]), unit(MT.CONTENT, ST_CC.TEXT, flip(rng, fam[2]["content"], 9)),
+                         unit(MT.DATA, 0, fam[2]["data"][:24]), unit(MT.INSTANCE, 0, fam[2]["inst"][:8]), unit(MT.INSTANCE, 0, fam[3]["inst"])]}
+    record("add_assets", {"assets": [two_len]}, lambda: add([two_len]))
+    q_two = {"units": [unit(MT.CONTENT, ST_CC.TEXT, fam[2]["content"][:16]), unit(MT.CONTENT, ST_CC.TEXT, flip(rng, fam[2]["content"], 30)),
+                       unit(MT.INSTANCE, 0, fam[3]["inst"][:16])]}
+    for limit in (100, 5, 1):
+        record("search_assets", {"query": q_two, "limit": limit}, lambda limit=limit: search(q_two, limit))
+    with_sp = next(a for a in assets[:40] if a.get("simprints") and "CONTENT_TEXT_V0" in a["simprints"])
+    stripped = {"iscc_id": with_sp["iscc_id"], "units": with_sp["units"][-2:], "metadata": {"name": "stripped"}}
+    record("add_assets", {"assets": [stripped]}, lambda: add([stripped]))
+    record("get_asset", {"iscc_id": with_sp["iscc_id"]}, lambda: idx.get_asset(with_sp["iscc_id"]).model_dump(mode="json", exclude_none=True))
+    sp_q = {"simprints": {"CONTENT_TEXT_V0": [e["simprint"] for e in with_sp["simprints"]["CONTENT_TEXT_V0"]]}}
+    for exact in (False, True):
+        record("search_assets", {"query": sp_q, "limit": 50, "exact": exact}, lambda exact=exact: search(sp_q, 50, exact))
+    record("search_assets", {"query": {"iscc_id": with_sp["iscc_id"]}, "limit": 50}, lambda: search({"iscc_id": with_sp["iscc_id"]}, 50))
+    # the same simprints re-sent in another order (fingerprint is order independent: no-op), then with one offset changed
+    sp_asset = next(a for a in assets[40:60] if a.get("simprints") and len(next(iter(a["simprints"].values()))) > 1)
+    t0 = next(iter(sp_asset["simprints"]))
+    reordered = dict(sp_asset, simprints={t0: list(reversed(sp_asset["simprints"][t0]))})
+    record("add_assets", {"assets": [reordered]}, lambda: add([reordered]))
+    moved = dict(sp_asset, simprints={t0: [dict(sp_asset["simprints"][t0][0], offset=4242)] + sp_asset["simprints"][t0][1:]})
+    record("add_assets", {"assets": [moved]}, lambda: add([moved]))
+    mv_q = {"simprints": {t0: [e["simprint"] for e in sp_asset["simprints"][t0]]}}
+    for exact in (False, True):
+        record("search_assets", {"query": mv_q, "limit": 10, "exact": exact}, lambda exact=exact: search(mv_q, 10, exact))
+    # a large batch with many updates at once
+    many = [dict(a, metadata={"name": f"bulk {i}", "n": i}) for i, a in enumerate(assets[10:35])]
+    record("add_assets", {"assets": many}, lambda: add(many))
+    for q in queries[:6]:
+        record("search_assets", {"query": q, "limit": 7}, lambda q=q: search(q, 7))
 
     # re-open (persistence): same answers after close + open
     record("len", {}, lambda: len(idx))

@@ -30,8 +30,9 @@ def _same_global(got, exp, limit):
     assert by_id(got) == by_id(exp)
 
 
-def replay(tmp_path, **index_kwargs):
-    steps = json.loads(GOLDEN.read_text())["steps"]
+def replay(tmp_path, steps=None, **index_kwargs):
+    if steps is None:
+        steps = json.loads(GOLDEN.read_text())["steps"]
     idx = B200Index(tmp_path / "flow", realm_id=None, max_dim=256, **index_kwargs)
     counts = {}
     for n, step in enumerate(steps):
