@@ -38,3 +38,43 @@ def test_backend_reproduces_the_live_reference(seed, tmp_path, cpu_stores):
     assert sum(1 for s in steps if s["op"] == "search_assets") > 100
     counts = replay(tmp_path / "ours", steps=steps)
     assert counts["add_assets"] >= 6
+
+
+@pytest.mark.parametrize("seed", [21, 22])
+def test_vector_store_classes_drop_into_the_live_reference(seed, tmp_path, cpu_stores, monkeypatch):
+    """
+    The B2 seam: the reference's own `UsearchIndex` / `UsearchSimprintIndex` code drives THIS
+    package's `ShardedNphdIndex` / `ShardedIndex128` in place of `iscc_usearch` - constructor arguments, add / remove /
+    contains / search / size / dirty / save / reset / close exactly as the reference calls them - and must produce the
+    same flow as with the exact stand-in the fixture was generated with.
+    """
+    import sys
+
+    import iscc_search_b200
+
+    gen, (index_mod, schema) = _generator()
+    expected = json.loads(json.dumps(gen.run(index_mod, schema, tmp_path / "stub", seed=seed)))
+    core = sys.modules["iscc_search.indexes.simprint.usearch_core"]
+    made = {"nphd": 0, "i128": 0, "searches": 0}
+
+    class Nphd(iscc_search_b200.ShardedNphdIndex):
+        def __init__(self, *a, **kw):
+            made["nphd"] += 1
+            super().__init__(*a, **kw)
+
+        def search(self, *a, **kw):
+            made["searches"] += 1
+            return super().search(*a, **kw)
+
+    class I128(iscc_search_b200.ShardedIndex128):
+        def __init__(self, *a, **kw):
+            made["i128"] += 1
+            super().__init__(*a, **kw)
+
+    monkeypatch.setattr(index_mod, "ShardedNphdIndex", Nphd)
+    monkeypatch.setattr(core, "ShardedIndex128", I128)
+    got = json.loads(json.dumps(gen.run(index_mod, schema, tmp_path / "ours", seed=seed)))
+    assert made["nphd"] >= 6 and made["i128"] >= 4 and made["searches"] > 100  # three unit types and two simprint types, opened twice
+    assert len(got) == len(expected)
+    for n, (g, e) in enumerate(zip(got, expected)):
+        assert g == e, f"step {n} ({e['op']})"
