@@ -486,7 +486,7 @@ def dump_result(res):
     return {"query": d["query"], "global_matches": d.get("global_matches", []), "chunk_matches": d.get("chunk_matches", [])}
 
 
-def run(index_mod, schema, tmp, seed=20261019, n_assets=70):
+def run(index_mod, schema, tmp, seed=20261019, n_assets=70, **options):
     rng = np.random.default_rng(seed)
     MT, ST_CC = codec.MT, codec.ST_CC
     steps = []
@@ -497,7 +497,7 @@ def run(index_mod, schema, tmp, seed=20261019, n_assets=70):
         except (ValueError, FileNotFoundError, FileExistsError) as e:
             steps.append({"op": op, "args": args, "error": type(e).__name__, "message": str(e)})
 
-    idx = index_mod.UsearchIndex(tmp / "flow", realm_id=None, max_dim=256)
+    idx = index_mod.UsearchIndex(tmp / "flow", realm_id=None, max_dim=256, **options)
     assets, fam = make_assets(rng, n_assets)
     E = schema.IsccEntry
 
@@ -599,7 +599,7 @@ def run(index_mod, schema, tmp, seed=20261019, n_assets=70):
     # re-open (persistence): same answers after close + open
     record("len", {}, lambda: len(idx))
     idx.close()
-    idx = index_mod.UsearchIndex(tmp / "flow", max_dim=256)
+    idx = index_mod.UsearchIndex(tmp / "flow", max_dim=256, **options)
     record("reopen", {}, lambda: {"assets": len(idx), "realm_id": idx._realm_id})
     record("search_assets", {"query": queries[0], "limit": 100}, lambda: search(queries[0], 100))
     record("get_asset", {"iscc_id": assets[45]["iscc_id"]}, lambda: idx.get_asset(assets[45]["iscc_id"]).model_dump(mode="json", exclude_none=True))

@@ -78,3 +78,15 @@ def test_vector_store_classes_drop_into_the_live_reference(seed, tmp_path, cpu_s
     assert len(got) == len(expected)
     for n, (g, e) in enumerate(zip(got, expected)):
         assert g == e, f"step {n} ({e['op']})"
+
+
+@pytest.mark.parametrize("options", [
+    {"match_threshold_units": 0.5, "confidence_exponent": 1, "match_threshold_simprints": 0.5},
+    {"match_threshold_units": 0.9, "confidence_exponent": 2, "oversampling_factor": 2},
+    {"match_threshold_units": 0.0, "match_threshold_simprints": 0.0},
+    {"match_threshold_units": 1.0, "match_threshold_simprints": 1.0, "oversampling_factor": 1},
+], ids=lambda o: "-".join(f"{k[6:9]}{v}" for k, v in o.items()))
+def test_backend_reproduces_the_live_reference_under_option_overrides(options, tmp_path, cpu_stores):
+    gen, (index_mod, schema) = _generator()
+    steps = json.loads(json.dumps(gen.run(index_mod, schema, tmp_path / "reference", seed=31, **options)))
+    replay(tmp_path / "ours", steps=steps, **options)
