@@ -118,8 +118,10 @@ class _Cursor:
         return self._ok()
 
     def next_nodup(self):
-        if not self._ok():
+        if self.pos is None:
             return self.first()
+        if not self._ok():
+            return False
         key = self.db.items[self.pos][0]
         while self._ok() and self.db.items[self.pos][0] == key:
             self.pos += 1
@@ -160,13 +162,17 @@ class _Cursor:
         return len(pairs), added
 
     def iternext_dup(self, keys=False, values=True):
+        # like py-lmdb: yields the current item and the following duplicates of its key; the cursor is left ON the last one
         if not self._ok():
             return
         key = self.db.items[self.pos][0]
-        while self._ok() and self.db.items[self.pos][0] == key:
+        while True:
             it = self.db.items[self.pos]
             yield (it[0], it[2]) if keys and values else (it[2] if values else it[0])
-            self.pos += 1
+            if self.pos + 1 < len(self.db.items) and self.db.items[self.pos + 1][0] == key:
+                self.pos += 1
+            else:
+                return
 
     def __iter__(self):
         if self.pos is None:

@@ -90,3 +90,47 @@ def test_backend_reproduces_the_live_reference_under_option_overrides(options, t
     gen, (index_mod, schema) = _generator()
     steps = json.loads(json.dumps(gen.run(index_mod, schema, tmp_path / "reference", seed=31, **options)))
     replay(tmp_path / "ours", steps=steps, **options)
+
+
+def test_import_of_a_reference_index_directory(tmp_path, cpu_stores):
+    """
+    Migration (iscc_search_b200/migrate.py): the LMDB tables a reference index leaves behind are replayed into this
+    backend's asset log; the imported index must answer like the reference does after its own `rebuild()` (both then
+    hold exactly what the source of truth describes - the reference's live derived indexes may carry stale vectors).
+    """
+    from iscc_search_b200 import schema as our_schema
+    from iscc_search_b200.backend import B200Index
+    from iscc_search_b200.migrate import import_lmdb_env
+    from tests.protocol_replay import _dump, _same_global
+
+    gen, (index_mod, schema) = _generator()
+    steps = json.loads(json.dumps(gen.run(index_mod, schema, tmp_path / "reference", seed=41)))
+    searches = [s["args"] for s in steps if s["op"] == "search_assets" and "result" in s]
+    ref = index_mod.UsearchIndex(tmp_path / "reference" / "flow", max_dim=256)
+    rebuilt = ref.rebuild(ref.tracked_unit_types, ref.tracked_simprint_types)
+    assert len(rebuilt["unit_types"]) >= 3 and len(rebuilt["simprint_types"]) == 2
+
+    env = gen._ENVS[str(tmp_path / "reference" / "flow" / "index.lmdb")]
+    info = import_lmdb_env(env, tmp_path / "imported")
+    assert info["assets"] == len(ref) and info["realm_id"] == 0 and sorted(info["simprint_types"]) == sorted(rebuilt["simprint_types"])
+    with pytest.raises(FileExistsError):
+        import_lmdb_env(env, tmp_path / "imported")
+    ours = B200Index(tmp_path / "imported")
+    assert len(ours) == len(ref) and ours._realm_id == 0
+    assert ours.tracked_unit_types == sorted(rebuilt["unit_types"]) and ours.tracked_simprint_types == sorted(rebuilt["simprint_types"])
+    for args in searches:
+        exp = gen.dump_result(ref.search_assets(schema.IsccQuery(**args["query"]), limit=args["limit"], exact=args.get("exact", False)))
+        got = _dump(ours.search_assets(our_schema.IsccQuery(**args["query"]), limit=args["limit"], exact=args.get("exact", False)))
+        assert got["query"] == exp["query"]
+        _same_global(got["global_matches"], exp["global_matches"], args["limit"])
+        assert got["chunk_matches"] == exp["chunk_matches"]
+    a = steps[0]["args"]["assets"][0]
+    assert ours.get_asset(a["iscc_id"]).model_dump(mode="json", exclude_none=True) == ref.get_asset(a["iscc_id"]).model_dump(mode="json", exclude_none=True)
+    # an identical re-add after the import is a no-op (fingerprints were carried over), a changed one an update
+    E = our_schema.IsccEntry
+    with_sp = next(x for x in reversed(steps[5]["args"]["assets"]) if x.get("simprints"))
+    dirty = {t: ix.dirty for t, ix in ours._simprint_indexes.items()}
+    assert ours.add_assets([E(**with_sp)])[0].status == "updated"
+    assert {t: ix.dirty for t, ix in ours._simprint_indexes.items()} == dirty
+    ours.close()
+    ref.close()
