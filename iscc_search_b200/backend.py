@@ -732,3 +732,22 @@ class B200IndexManager:
         component_bytes.update(idx.derived_sizes)
         mb = 1024 * 1024
         return sum(component_bytes.values()) // mb, {name: size // mb for name, size in component_bytes.items()}
+
+
+def get_index(uri, **options):
+    # type: (str, object) -> B200IndexManager
+    """
+    `b200:///path[?device=0,1,2,3]` -> `B200IndexManager` - the branch iscc-search's `options.get_index()`
+    (options.py:327-375) needs next to `lmdb://` and `usearch://`. Options are the `DEFAULT_OPTIONS` keys.
+    """
+    from urllib.parse import parse_qs, urlparse
+
+    parsed = urlparse(uri)
+    if parsed.scheme != "b200":
+        raise ValueError(f"Unsupported index URI scheme: '{uri}'. Expected b200:///path")
+    path = parsed.path[1:] if parsed.path.startswith("//") else parsed.path
+    if not path:
+        raise ValueError(f"Index URI '{uri}' names no directory")
+    query = parse_qs(parsed.query)
+    devices = [int(d) for d in ",".join(query.get("device", ["0"])).split(",") if d != ""]
+    return B200IndexManager(path, device=devices if len(devices) > 1 else devices[0], **options)

@@ -32,7 +32,12 @@ def rnd(seed, n):
 
 
 def case_index_lifecycle(tmp_path):
-    m = B200IndexManager(tmp_path)
+    from iscc_search_b200.backend import get_index
+
+    m = get_index(f"b200://{tmp_path}?device=0", match_threshold_units=0.8)
+    assert isinstance(m, B200IndexManager) and m.base_path == tmp_path and m._options == {"match_threshold_units": 0.8}
+    with pytest.raises(ValueError, match="scheme"):
+        get_index("usearch:///somewhere")
     assert m.list_indexes() == []
     created = m.create_index(IsccIndex(name="test"))
     assert (created.name, created.assets, created.size) == ("test", 0, 0)
