@@ -252,8 +252,7 @@ class B200Index:
             if self._realm_id is None:  # inferred from the first asset (index.py:239-252)
                 if assets[0].iscc_id is None:
                     raise ValueError("Asset must have iscc_id field when adding to index")
-                self._realm_id = entries.extract_realm_id(assets[0].iscc_id)
-                self._log.set_realm(self._realm_id)
+                self._realm_id = entries.extract_realm_id(assets[0].iscc_id)  # persisted below, once the batch is accepted
 
             # validate the whole batch before the first mutation (the reference's LMDB transaction would roll back)
             for asset in assets:
@@ -268,6 +267,9 @@ class B200Index:
                     )
                 for unit_str in asset.units or []:
                     IsccUnit(unit_str).unit_type
+
+            if self._log.realm_id != self._realm_id:
+                self._log.set_realm(self._realm_id)
 
             nphd_batches = {}     # unit_type -> ([keys], [bodies])
             nphd_updated_keys = set()
