@@ -119,7 +119,7 @@ class B200Index:
         """(unit_type -> {key: longest body}, [(key, INSTANCE body)]) from the asset log."""
         best, instance = {}, []
         for key, asset_bytes in self._log.assets.items():
-            for unit_str in entries.deserialize_asset(asset_bytes).units or []:
+            for unit_str in json.loads(asset_bytes).get("units") or []:  # plain JSON: this runs over every asset on open
                 unit = IsccUnit(unit_str)
                 if unit.unit_type.startswith("INSTANCE_"):
                     instance.append((key, unit.body))
