@@ -69,15 +69,25 @@ static const uint64_t LCM_BITS = 8ull * 144403552893600ull;
 
 static inline uint64_t load64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }
 
-/* Hamming distance over the first m bytes (1..32) of two 32-byte zero padded rows. */
-static inline uint32_t prefix_hamming(const uint8_t* a, const uint8_t* q, uint32_t m) {
-    uint32_t full = m >> 3, rem = m & 7, h = 0;
-    for (uint32_t w = 0; w < full; w++) h += (uint32_t)__builtin_popcountll(load64(a + 8 * w) ^ load64(q + 8 * w));
-    if (rem) {
-        uint64_t mask = (1ull << (8 * rem)) - 1; /* little-endian load: first bytes are the low ones */
-        h += (uint32_t)__builtin_popcountll((load64(a + 8 * full) ^ load64(q + 8 * full)) & mask);
-    }
-    return h;
+/* Hamming distance over the first m bytes (1..32) of two 32-byte zero padded rows: four masked 64-bit popcounts,
+ * no branches (the prefix mask of every length is tabulated once). */
+static uint64_t g_mask[MAXB + 1][4];
+static int g_mask_ready = 0;
+static void init_masks(void) {
+    for (uint32_t m = 0; m <= MAXB; m++)
+        for (uint32_t w = 0; w < 4; w++) {
+            uint32_t lo = 8 * w;
+            uint64_t mask = 0;
+            if (m >= lo + 8) mask = ~0ull;
+            else if (m > lo) mask = (1ull << (8 * (m - lo))) - 1; /* little-endian load: first bytes are the low ones */
+            g_mask[m][w] = mask;
+        }
+    g_mask_ready = 1;
+}
+static inline uint32_t prefix_hamming(const uint8_t* a, const uint64_t q[4], uint32_t m) {
+    const uint64_t* mk = g_mask[m];
+    return (uint32_t)(__builtin_popcountll((load64(a) ^ q[0]) & mk[0]) + __builtin_popcountll((load64(a + 8) ^ q[1]) & mk[1]) +
+                      __builtin_popcountll((load64(a + 16) ^ q[2]) & mk[2]) + __builtin_popcountll((load64(a + 24) ^ q[3]) & mk[3]));
 }
 
 /*
@@ -97,6 +107,7 @@ int oracle_nphd_topk(const uint8_t* codes, const uint8_t* lens, const uint64_t* 
     if (n_threads > 0) omp_set_num_threads(n_threads);
 #endif
     int bad = 0;
+    if (!g_mask_ready) init_masks();
 #pragma omp parallel for schedule(dynamic, 1)
     for (long qi = 0; qi < (long)q; qi++) {
         cand_t* hp = (cand_t*)malloc(sizeof(cand_t) * k);
@@ -106,10 +117,12 @@ int oracle_nphd_topk(const uint8_t* codes, const uint8_t* lens, const uint64_t* 
         if (ql < 1 || ql > MAXB || !hp) { bad = 1; counts[qi] = 0; free(hp); continue; }
         uint64_t scale[MAXB + 1];
         for (uint32_t m = 1; m <= MAXB; m++) scale[m] = LCM_BITS / (8ull * m);
+        uint64_t qw[4];
+        for (int w = 0; w < 4; w++) qw[w] = load64(qv + 8 * w);
         uint64_t worst = UINT64_MAX; /* dnum of heap root once the heap is full */
         for (size_t i = 0; i < n; i++) {
             uint32_t m = lens[i] < ql ? lens[i] : ql;
-            uint32_t h = prefix_hamming(codes + i * MAXB, qv, m);
+            uint32_t h = prefix_hamming(codes + i * MAXB, qw, m);
             uint64_t dnum = (uint64_t)h * scale[m];
             if (dnum > worst) continue;                       /* cheap reject once k are held */
             if (thr_den && (uint64_t)h * thr_den > (uint64_t)thr_num * 8ull * m) continue;
