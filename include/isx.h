@@ -186,6 +186,9 @@ int isx_share_reset(isx_store_t* s);
  */
 int isx_selftest_rank_table(uint32_t class_mask, uint16_t* rank_out, uint16_t* hmax_out, uint32_t hmax_stride, uint32_t* R_out);
 int isx_selftest_keymap(uint64_t n_ops, uint64_t seed, uint32_t key_space);
+/*   isx_selftest_distance    the scan kernels' arithmetic helpers (carry-save distance, OR-fold lower bounds), built for the
+ *                            host from the same template code, against a naive popcount on n random rows per word count */
+int isx_selftest_distance(uint64_t n, uint64_t seed);
 
 /* largest k isx_search accepts for this store (shared-memory bound of the final selection) */
 int isx_max_k(isx_store_t* s, uint32_t* k_out);

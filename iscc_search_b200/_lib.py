@@ -51,7 +51,7 @@ SYMBOLS = (
     "isx_set_profiling", "isx_get_stats", "isx_add", "isx_remove", "isx_contains", "isx_get", "isx_size",
     "isx_clear", "isx_device_bytes", "isx_length_mask", "isx_save", "isx_load", "isx_search",
     "isx_search_device", "isx_merge_device", "isx_max_k", "isx_match_all", "isx_share_init", "isx_share_attach",
-    "isx_share_reset", "isx_selftest_rank_table", "isx_selftest_keymap",
+    "isx_share_reset", "isx_selftest_rank_table", "isx_selftest_keymap", "isx_selftest_distance",
 )
 
 
@@ -110,6 +110,7 @@ def lib():
     L.isx_share_reset.argtypes = [vp]
     L.isx_selftest_rank_table.argtypes = [u32, vp, vp, u32, P(u32)]
     L.isx_selftest_keymap.argtypes = [u64, u64, u32]
+    L.isx_selftest_distance.argtypes = [u64, u64]
     for name in SYMBOLS:
         if name != "isx_last_error":
             getattr(L, name).restype = ci

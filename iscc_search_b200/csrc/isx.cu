@@ -1252,6 +1252,56 @@ int isx_selftest_rank_table(uint32_t class_mask, uint16_t* rank_out, uint16_t* h
     return 0;
 }
 
+}  // extern "C" (templates cannot have C linkage)
+
+// Host build of the device arithmetic helpers (kernels.cuh: pair_distance, LowerBound::eval) against a naive popcount.
+template <int WE>
+static int selftest_distance_we(uint64_t n, uint64_t& x) {
+    auto next = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    static const uint32_t masks[4] = {0xffffffffu, 0x000000ffu, 0x0000ffffu, 0x00ffffffu};
+    for (uint64_t it = 0; it < n; it++) {
+        uint4 a[WE];
+        uint32_t qv[WE];
+        const uint32_t sparse = (uint32_t)(it % 3);  // dense random words, near-identical rows, identical rows
+        for (int w = 0; w < WE; w++) {
+            qv[w] = (uint32_t)next();
+            uint32_t r[4];
+            for (int k = 0; k < 4; k++) {
+                uint64_t v = next();
+                r[k] = sparse == 0 ? (uint32_t)v : sparse == 1 ? (qv[w] ^ (uint32_t)(v & (v >> 16) & (v >> 32))) : qv[w];
+            }
+            a[w] = make_uint4(r[0], r[1], r[2], r[3]);
+        }
+        const uint32_t mask_last = masks[it & 3];
+        for (int r = 0; r < 4; r++) {
+            uint32_t xw[WE], exact = 0, fold2 = 0, fold3 = 0;
+            for (int w = 0; w < WE; w++) {
+                xw[w] = (comp(a[w], r) ^ qv[w]) & (w == WE - 1 ? mask_last : 0xffffffffu);
+                exact += (uint32_t)__builtin_popcount(xw[w]);
+            }
+            for (int w = 0; w < WE; w += 2) fold2 += (uint32_t)__builtin_popcount(xw[w] | (w + 1 < WE ? xw[w + 1] : 0u));
+            for (int w = 0; w < WE; w += 3) fold3 += (uint32_t)__builtin_popcount(xw[w] | (w + 1 < WE ? xw[w + 1] : 0u) | (w + 2 < WE ? xw[w + 2] : 0u));
+            if (pair_distance<WE>(xw) != exact) return fail(ISX_EINVAL, "pair_distance<%d> differs from the naive popcount", WE);
+            const uint32_t b2 = LowerBound<WE>::template eval<2>(a, qv, r, mask_last), b3 = LowerBound<WE>::template eval<3>(a, qv, r, mask_last);
+            if (b2 != fold2 || b3 != fold3) return fail(ISX_EINVAL, "LowerBound<%d>::eval differs from the naive OR fold", WE);
+            if (b2 > exact || b3 > exact) return fail(ISX_EINVAL, "LowerBound<%d> is not a lower bound", WE);
+        }
+    }
+    return 0;
+}
+
+extern "C" {
+
+int isx_selftest_distance(uint64_t n, uint64_t seed) {
+    uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1;
+    int rc = 0;
+    if ((rc = selftest_distance_we<1>(n, x)) || (rc = selftest_distance_we<2>(n, x)) || (rc = selftest_distance_we<3>(n, x)) ||
+        (rc = selftest_distance_we<4>(n, x)) || (rc = selftest_distance_we<5>(n, x)) || (rc = selftest_distance_we<6>(n, x)) ||
+        (rc = selftest_distance_we<7>(n, x)) || (rc = selftest_distance_we<8>(n, x)))
+        return rc;
+    return 0;
+}
+
 int isx_selftest_keymap(uint64_t n_ops, uint64_t seed, uint32_t key_space) {
     // random insert / update / erase / find against a std::vector reference over a small key space (many collisions
     // of home slots and long probe chains: exercises the backward-shift deletion)

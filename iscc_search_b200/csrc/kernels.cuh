@@ -157,31 +157,46 @@ __device__ __forceinline__ void tighten_tau(const ScanParams& p, uint32_t q, uin
 // Carry-save compression: the POPC pipe issues 16 lanes/clk/SM against 64 for LOP3 and both overlap
 // (profiles/microbench), so three XOR words are first folded by a full adder (2 LOP3) into a sum and a
 // carry word: popc(x0)+popc(x1)+popc(x2) = popc(s) + 2*popc(c). 8 words need 5 POPC instead of 8.
+// The pure arithmetic helpers below are __host__ __device__ so that the library's host-side self test
+// (isx_selftest_distance, CPU test-suite) runs the very same template code against a naive popcount.
+#ifdef __CUDA_ARCH__
+#define ISX_UNROLL _Pragma("unroll")
+#else
+#define ISX_UNROLL
+#endif
+__host__ __device__ __forceinline__ uint32_t popc32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__popc(x);
+#else
+    return (uint32_t)__builtin_popcount(x);
+#endif
+}
+
 template <int WE>
-__device__ __forceinline__ uint32_t pair_distance(const uint32_t (&x)[WE]) {
+__host__ __device__ __forceinline__ uint32_t pair_distance(const uint32_t (&x)[WE]) {
     auto csa_s = [](uint32_t a, uint32_t b, uint32_t c) { return a ^ b ^ c; };
     auto csa_c = [](uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a ^ b)); };
-    if constexpr (WE == 1) return __popc(x[0]);
-    else if constexpr (WE == 2) return __popc(x[0]) + __popc(x[1]);
-    else if constexpr (WE == 3) return __popc(csa_s(x[0], x[1], x[2])) + 2 * __popc(csa_c(x[0], x[1], x[2]));
-    else if constexpr (WE == 4) return __popc(csa_s(x[0], x[1], x[2])) + __popc(x[3]) + 2 * __popc(csa_c(x[0], x[1], x[2]));
+    if constexpr (WE == 1) return popc32(x[0]);
+    else if constexpr (WE == 2) return popc32(x[0]) + popc32(x[1]);
+    else if constexpr (WE == 3) return popc32(csa_s(x[0], x[1], x[2])) + 2 * popc32(csa_c(x[0], x[1], x[2]));
+    else if constexpr (WE == 4) return popc32(csa_s(x[0], x[1], x[2])) + popc32(x[3]) + 2 * popc32(csa_c(x[0], x[1], x[2]));
     else if constexpr (WE == 5)
-        return __popc(csa_s(x[0], x[1], x[2])) + __popc(x[3]) + __popc(x[4]) + 2 * __popc(csa_c(x[0], x[1], x[2]));
+        return popc32(csa_s(x[0], x[1], x[2])) + popc32(x[3]) + popc32(x[4]) + 2 * popc32(csa_c(x[0], x[1], x[2]));
     else if constexpr (WE == 6)
-        return __popc(csa_s(x[0], x[1], x[2])) + __popc(csa_s(x[3], x[4], x[5])) +
-               2 * (__popc(csa_c(x[0], x[1], x[2])) + __popc(csa_c(x[3], x[4], x[5])));
+        return popc32(csa_s(x[0], x[1], x[2])) + popc32(csa_s(x[3], x[4], x[5])) +
+               2 * (popc32(csa_c(x[0], x[1], x[2])) + popc32(csa_c(x[3], x[4], x[5])));
     else if constexpr (WE == 7) {
         uint32_t s0 = csa_s(x[0], x[1], x[2]), s1 = csa_s(x[3], x[4], x[5]);
-        return __popc(csa_s(s0, s1, x[6])) +
-               2 * (__popc(csa_c(x[0], x[1], x[2])) + __popc(csa_c(x[3], x[4], x[5])) + __popc(csa_c(s0, s1, x[6])));
+        return popc32(csa_s(s0, s1, x[6])) +
+               2 * (popc32(csa_c(x[0], x[1], x[2])) + popc32(csa_c(x[3], x[4], x[5])) + popc32(csa_c(s0, s1, x[6])));
     } else {
         uint32_t s0 = csa_s(x[0], x[1], x[2]), s1 = csa_s(x[3], x[4], x[5]);
-        return __popc(csa_s(s0, s1, x[6])) + __popc(x[7]) +
-               2 * (__popc(csa_c(x[0], x[1], x[2])) + __popc(csa_c(x[3], x[4], x[5])) + __popc(csa_c(s0, s1, x[6])));
+        return popc32(csa_s(s0, s1, x[6])) + popc32(x[7]) +
+               2 * (popc32(csa_c(x[0], x[1], x[2])) + popc32(csa_c(x[3], x[4], x[5])) + popc32(csa_c(s0, s1, x[6])));
     }
 }
 
-__device__ __forceinline__ uint32_t comp(const uint4& v, int r) { return r == 0 ? v.x : r == 1 ? v.y : r == 2 ? v.z : v.w; }
+__host__ __device__ __forceinline__ uint32_t comp(const uint4& v, int r) { return r == 0 ? v.x : r == 1 ? v.y : r == 2 ? v.z : v.w; }
 
 // Cheap LOWER bounds of the distance: popc(x0 | x1 [| x2]) <= popc(x0) + popc(x1) [+ popc(x2)], one POPC per
 // group of F words (the OR rides in the XOR's LOP3). A row whose bound already exceeds the query's current
@@ -197,12 +212,12 @@ struct LowerBound {
     static constexpr uint32_t kCutoff2 = WE == 2 ? 17u : WE == 4 ? 38u : WE == 5 ? 50u : WE == 6 ? 60u : WE == 8 ? 82u : 0u;
     // bound of row r of a 4-row group straight from the planes
     template <int F>
-    __device__ __forceinline__ static uint32_t eval(const uint4 (&a)[WE], const uint32_t (&qv)[WE], int r, uint32_t mask_last) {
+    __host__ __device__ __forceinline__ static uint32_t eval(const uint4 (&a)[WE], const uint32_t (&qv)[WE], int r, uint32_t mask_last) {
         uint32_t acc = 0;
-#pragma unroll
+        ISX_UNROLL
         for (int w = 0; w < WE; w += F) {
             uint32_t t = 0;
-#pragma unroll
+            ISX_UNROLL
             for (int j = 0; j < F; j++) {
                 if (w + j < WE) {
                     uint32_t x = comp(a[w + j], r) ^ qv[w + j];
@@ -210,7 +225,7 @@ struct LowerBound {
                     t |= x;
                 }
             }
-            acc += __popc(t);
+            acc += popc32(t);
         }
         return acc;
     }

@@ -54,3 +54,11 @@ def test_keymap_randomized_against_reference():
     for seed, ops, space in ((1, 200_000, 64), (2, 300_000, 1500), (3, 400_000, 50_000)):
         rc = L.isx_selftest_keymap(ops, seed, space)
         assert rc == 0, L.isx_last_error()
+
+
+def test_device_arithmetic_helpers_on_the_host():
+    # the same template code the scan kernels use (carry-save distance, 2- and 3-word OR-fold bounds), compiled for the host
+    L = _lib.lib()
+    for seed in (1, 2, 3):
+        rc = L.isx_selftest_distance(20_000, seed)
+        assert rc == 0, L.isx_last_error()
