@@ -95,6 +95,26 @@ int isx_get_stats(isx_store_t* s, isx_stats_t* out);
 /* added[i] = 1 if row i was stored, 0 if its key was already present (first wins, also inside the
  * batch) - tests/test_usearch_add.py:53-63.  added may be NULL. */
 int isx_add(isx_store_t* s, const void* keys, const uint8_t* codes, const uint8_t* lens, size_t n, uint8_t* added);
+/*
+ * Bulk append straight from DEVICE memory (warm start from a snapshot already in HBM, a partition produced by another
+ * GPU job, the synthetic 1 B-row data sets of SURVEY 8d): d_keys (n x key_bytes, same form as isx_add), d_codes
+ * (n x 32 bytes), d_lens (n length bytes, or NULL = every code has uniform_len bytes). The caller PROMISES that the
+ * keys are unique and not stored yet - no per-row host work happens here; the host key map is completed lazily by the
+ * first keyed call (add / remove / contains / get / save), which fails with ISX_EINVAL if the promise was broken.
+ * Replaces the add loop of a rebuild (iscc_search/indexes/usearch/index.py:1650-1726, lmdb_ops.py:304-343) for
+ * data that is already on the device. Row placement inside a bucket is unspecified (results never depend on it).
+ */
+int isx_add_device(isx_store_t* s, const void* d_keys, const uint8_t* d_codes, const uint8_t* d_lens, uint32_t uniform_len, size_t n);
+/*
+ * Bench / test facility, not part of the reference boundary: rows [start, start+n) of the synthetic data set of
+ * SURVEY.md 8d (definition: iscc_search_b200/synth.py) generated on the device, on the store's stream, into
+ * caller-owned device buffers in the form isx_add_device takes. key_mode 0: uint64 keys; 1: 16-byte simprint chunk
+ * pointers (chunks_per_asset chunks per asset). lengths: n_lengths (<= 8) code lengths, picked per row by a hash.
+ * dup_every > 0: every dup_every-th row repeats the code of the row dup_back before it. d_lens may be NULL.
+ */
+int isx_synth_rows_device(isx_store_t* s, uint64_t seed, uint64_t start, size_t n, const uint8_t* lengths, uint32_t n_lengths,
+                          uint32_t key_mode, uint32_t chunks_per_asset, uint32_t dup_every, uint32_t dup_back, void* d_keys,
+                          uint8_t* d_codes, uint8_t* d_lens);
 /* removed[i] = 1 if the key was present - tests/test_usearch_remove.py:19-48.  May be NULL. */
 int isx_remove(isx_store_t* s, const void* keys, size_t n, uint8_t* removed, uint64_t* n_removed);
 int isx_contains(isx_store_t* s, const void* keys, size_t n, uint8_t* present);
@@ -169,14 +189,20 @@ int isx_match_all(isx_store_t* s, const uint8_t* query, uint32_t qlen, uint32_t 
  * the per-shard work proportional to its rows. Results are unchanged (the merged top-k is exact either way).
  *   isx_share_init   allocate + export this rank's histograms (handle_out: 64 bytes, cudaIpcMemHandle_t)
  *   isx_share_attach map a peer's histograms (handle from its isx_share_init)
- *   isx_share_reset  enqueue zeroing of the home histograms on the store's stream. Protocol per batch, same on
- *                    every rank: isx_share_reset -> a collective on the same stream (barrier) ->
+ *   isx_share_reset  enqueue zeroing of the home histograms on the store's stream and ARM the next search.
+ *                    Protocol per batch, same on every rank: isx_share_reset -> a collective on the same stream
+ *                    (barrier; the host layer all-reduces the stored-length masks there) -> isx_share_set_lengths ->
  *                    isx_search_device (identical queries, qlens, k on all ranks) -> all-gather + isx_merge_device.
+ *                    A search that was not armed by a reset (isx_search, match_all, ...) never touches the shared state.
+ *   isx_share_set_lengths  union over ALL ranks of isx_length_mask. The shared histograms are indexed by the dense
+ *                    rank of h/nbits among the compared-length classes, so every rank must derive its rank table
+ *                    from the same classes even when its own shard lacks a length bucket.
  * Sharing is used only when all of world > 1, q <= max_queries and the distance classes fit (<= 512 ranks).
  */
 int isx_share_init(isx_store_t* s, uint32_t world, uint32_t rank, uint32_t max_queries, void* handle_out);
 int isx_share_attach(isx_store_t* s, uint32_t peer_rank, const void* handle);
 int isx_share_reset(isx_store_t* s);
+int isx_share_set_lengths(isx_store_t* s, uint32_t global_length_mask);
 
 /*
  * Host-only self tests (no CUDA device needed; used by the CPU test-suite):

@@ -48,10 +48,10 @@ _lib = None
 # every symbol include/isx.h declares (tests check the .so exports all of them)
 SYMBOLS = (
     "isx_last_error", "isx_abi_version", "isx_device_count", "isx_open", "isx_close", "isx_set_stream",
-    "isx_set_profiling", "isx_get_stats", "isx_add", "isx_remove", "isx_contains", "isx_get", "isx_size",
+    "isx_set_profiling", "isx_get_stats", "isx_add", "isx_add_device", "isx_synth_rows_device", "isx_remove", "isx_contains", "isx_get", "isx_size",
     "isx_clear", "isx_device_bytes", "isx_length_mask", "isx_save", "isx_load", "isx_search",
     "isx_search_device", "isx_merge_device", "isx_max_k", "isx_match_all", "isx_share_init", "isx_share_attach",
-    "isx_share_reset", "isx_selftest_rank_table", "isx_selftest_keymap", "isx_selftest_distance",
+    "isx_share_reset", "isx_share_set_lengths", "isx_selftest_rank_table", "isx_selftest_keymap", "isx_selftest_distance",
 )
 
 
@@ -92,6 +92,8 @@ def lib():
     L.isx_get_stats.argtypes = [vp, P(IsxStats)]
     L.isx_add.argtypes = [vp, vp, vp, vp, sz, vp]
     L.isx_remove.argtypes = [vp, vp, sz, vp, P(u64)]
+    L.isx_add_device.argtypes = [vp, vp, vp, vp, u32, sz]
+    L.isx_synth_rows_device.argtypes = [vp, u64, u64, sz, vp, u32, u32, u32, u32, u32, vp, vp, vp]
     L.isx_contains.argtypes = [vp, vp, sz, vp]
     L.isx_get.argtypes = [vp, vp, sz, vp, vp]
     L.isx_size.argtypes = [vp, P(u64)]
@@ -108,6 +110,7 @@ def lib():
     L.isx_share_init.argtypes = [vp, u32, u32, u32, vp]
     L.isx_share_attach.argtypes = [vp, u32, vp]
     L.isx_share_reset.argtypes = [vp]
+    L.isx_share_set_lengths.argtypes = [vp, u32]
     L.isx_selftest_rank_table.argtypes = [u32, vp, vp, u32, P(u32)]
     L.isx_selftest_keymap.argtypes = [u64, u64, u32]
     L.isx_selftest_distance.argtypes = [u64, u64]
@@ -199,6 +202,16 @@ class Store:
         added = np.zeros(n, dtype=np.uint8)
         check(lib().isx_add(self.handle, ptr(keys), ptr(codes), ptr(lens), n, ptr(added)))
         return added
+
+    def add_device(self, d_keys, d_codes, d_lens, n, uniform_len=0):
+        # type: (int, int, int|None, int, int) -> None
+        """Bulk append of n rows from DEVICE pointers; keys promised unique and absent (include/isx.h: isx_add_device)."""
+        check(lib().isx_add_device(self.handle, d_keys, d_codes, d_lens, uniform_len, n))
+
+    def synth_rows_device(self, seed, start, n, d_keys, d_codes, d_lens, lengths=(8, 16, 24, 32), key_mode=0, cpa=64, dup_every=0, dup_back=0):
+        """Rows [start, start+n) of the synthetic data set (synth.py) generated on the device into caller-owned buffers."""
+        ln = np.ascontiguousarray(lengths, dtype=np.uint8)
+        check(lib().isx_synth_rows_device(self.handle, seed, start, n, ptr(ln), len(ln), key_mode, cpa, dup_every, dup_back, d_keys, d_codes, d_lens))
 
     def remove(self, keys, n):
         removed = np.zeros(n, dtype=np.uint8)

@@ -6,6 +6,7 @@
 // the per-query rank threshold before the bulk of the store is streamed), exact fallback re-scan
 // for queries whose candidate buffer overflowed.
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -96,6 +97,7 @@ struct Segment {
     SegDesc desc{};
     uint32_t len_bytes = 0;
     std::vector<uint64_t> h_khi, h_klo;  // host mirror of the keys (needed to re-point the moved row on swap-remove)
+    uint32_t mirrored = 0;               // rows [0, mirrored) are in the host mirror and the key map (bulk appends lag behind)
     size_t bytes = 0;
 };
 
@@ -125,6 +127,9 @@ struct isx_store {
     std::mutex work_mu;         // serialises users of the scratch buffers below
 
     KeyMap map;
+    std::atomic<bool> map_stale{false};        // rows were bulk-appended from device memory (isx_add_device): the key map and
+                                               // the host key mirrors are completed lazily by the first keyed operation
+    uint64_t n_rows = 0;                       // live rows (== map.size() when the map is current)
     std::vector<Segment> segs;                 // global segment ids
     std::vector<uint32_t> bucket_segs[kMaxBytes + 1];
     uint64_t bucket_rows[kMaxBytes + 1] = {0};
@@ -147,9 +152,12 @@ struct isx_store {
     uint32_t* share_local = nullptr;              // this rank's home histograms (cudaMalloc, IPC exported)
     uint32_t* share_ptrs[kMaxRanks] = {nullptr};  // [r] = rank r's home histograms mapped into this process
     size_t share_bytes = 0;
+    uint32_t share_len_mask = 0;                  // union of the stored-length masks of ALL ranks (isx_share_set_lengths)
+    bool share_armed = false;                     // set by isx_share_reset, consumed by the next search: only a search that
+                                                  // follows reset + barrier may count into / read the shared histograms
 
     // scratch
-    DevBuf d_stage_codes, d_stage_keys, d_stage_dest, d_moves;
+    DevBuf d_stage_codes, d_stage_keys, d_stage_dest, d_moves, d_bulk;
     DevBuf d_queries, d_tau, d_hist, d_shist, d_cnt, d_ovf, d_cand, d_qmap, d_fb, d_fb_cand;
     DevBuf d_out_khi, d_out_klo, d_out_h, d_out_n, d_out_cnt, d_out_codes, d_bigsort;
     PinnedBuf h_queries, h_qmap, h_flags, h_out;
@@ -180,7 +188,7 @@ static int set_device(isx_store* s) {
     return 0;
 }
 
-static int new_segment(isx_store* s, uint32_t len_bytes, uint32_t cap) {
+static int new_segment(isx_store* s, uint32_t len_bytes, uint32_t cap, bool mirror = true) {
     if (s->segs.size() >= (1u << kSegBits)) return fail(ISX_ENOMEM, "segment table full (%u segments)", 1u << kSegBits);
     Segment sg;
     uint32_t words = (len_bytes + 3) / 4;
@@ -198,8 +206,10 @@ static int new_segment(isx_store* s, uint32_t len_bytes, uint32_t cap) {
     sg.desc.n = 0;
     sg.desc.len_bytes = len_bytes;
     sg.desc.words = words;
-    sg.h_khi.resize(cap);
-    if (s->key_bytes == 16) sg.h_klo.resize(cap);
+    if (mirror) {
+        sg.h_khi.resize(cap);
+        if (s->key_bytes == 16) sg.h_klo.resize(cap);
+    }
     s->device_bytes += total;
     s->bucket_segs[len_bytes].push_back((uint32_t)s->segs.size());
     s->segs.push_back(std::move(sg));
@@ -239,6 +249,40 @@ static int upload_blocks(isx_store* s) {
     }
     s->blocks_version = s->version;
     return 0;
+}
+
+// Complete the key map + host key mirrors after bulk appends (caller holds rows_mu exclusively and work_mu).
+static int sync_map(isx_store* s) {
+    if (!s->map_stale.load()) return 0;
+    CU(cudaSetDevice(s->device));
+    s->map.reserve(s->n_rows);
+    for (size_t sid = 0; sid < s->segs.size(); sid++) {
+        Segment& sg = s->segs[sid];
+        const uint32_t n = sg.desc.n, m0 = sg.mirrored;
+        if (m0 >= n) continue;
+        if (sg.h_khi.size() < sg.desc.cap) sg.h_khi.resize(sg.desc.cap);
+        if (s->key_bytes == 16 && sg.h_klo.size() < sg.desc.cap) sg.h_klo.resize(sg.desc.cap);
+        CU(cudaMemcpyAsync(sg.h_khi.data() + m0, sg.desc.khi + m0, (size_t)(n - m0) * 8, cudaMemcpyDeviceToHost, s->stream));
+        if (s->key_bytes == 16) CU(cudaMemcpyAsync(sg.h_klo.data() + m0, sg.desc.klo + m0, (size_t)(n - m0) * 8, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        for (uint32_t r = m0; r < n; r++) {
+            const Key128 key{sg.h_khi[r], s->key_bytes == 16 ? sg.h_klo[r] : 0};
+            if (!s->map.insert(key, ((uint64_t)sid << 32) | r))
+                return fail(ISX_EINVAL, "isx_add_device: bulk-appended keys were not unique (key %016llx%016llx is stored twice)",
+                            (unsigned long long)key.hi, (unsigned long long)key.lo);
+        }
+        sg.mirrored = n;
+    }
+    s->map_stale.store(false);
+    return 0;
+}
+
+// keyed operations call this BEFORE taking their own locks
+static int ensure_map(isx_store* s) {
+    if (!s->map_stale.load()) return 0;
+    std::unique_lock<std::shared_mutex> g(s->rows_mu);
+    std::lock_guard<std::mutex> gw(s->work_mu);
+    return sync_map(s);
 }
 
 // ---- rank tables -------------------------------------------------------------------------------
@@ -414,6 +458,8 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
                        uint32_t thr_num, uint32_t thr_den, const SearchOut& out) {
     isx_stats_t& st = s->stats;
     st = isx_stats_t{};
+    const bool share_armed = s->share_armed;  // consumed by this call whatever happens next
+    s->share_armed = false;
     if (Q == 0) return 0;
     if (k < 1) return fail(ISX_EINVAL, "`count` must be >= 1");
     const uint32_t key_words = s->key_bytes == 16 ? 2 : 1;
@@ -437,6 +483,9 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
     uint32_t qmask = 0, bmask = 0, cmask = 0;
     for (size_t i = 0; i < Q; i++) qmask |= 1u << (qlens[i] - 1);
     for (uint32_t L = 1; L <= kMaxBytes; L++) if (s->bucket_rows[L]) bmask |= 1u << (L - 1);
+    // Shared thresholds index the peer histograms by dense rank, so every rank must build the SAME rank table:
+    // the compared-length classes come from the union of the lengths stored on any rank, not from the local rows.
+    if (s->share_world > 1 && share_armed) bmask |= s->share_len_mask;
     for (uint32_t a = 1; a <= kMaxBytes; a++) {
         if (!(qmask & (1u << (a - 1)))) continue;
         cmask |= 1u << (a - 1);  // keeps the table non-empty for an empty store
@@ -537,7 +586,7 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
         }
 
     // shared (cross-rank) histograms need every rank to see the same query batch in the same order
-    const bool share_on = s->share_world > 1 && R <= isx_store::kShareRcap && Q <= s->share_maxq;
+    const bool share_on = s->share_world > 1 && share_armed && R <= isx_store::kShareRcap && Q <= s->share_maxq;
     auto make_params = [&](const Tile& t) {
         ScanParams p{};
         p.segs = s->d_segs.as<SegDesc>();
@@ -772,6 +821,8 @@ static void free_rows(isx_store* s) {
     memset(s->bucket_rows, 0, sizeof s->bucket_rows);
     s->device_bytes = 0;
     s->map.clear();
+    s->map_stale.store(false);
+    s->n_rows = 0;
     s->segs_dirty = true;
     s->version++;
 }
@@ -823,7 +874,7 @@ int isx_get_stats(isx_store_t* s, isx_stats_t* out) {
 int isx_size(isx_store_t* s, uint64_t* n_out) {
     if (!s || !n_out) return fail(ISX_EINVAL, "NULL argument");
     std::shared_lock<std::shared_mutex> g(s->rows_mu);
-    *n_out = s->map.size();
+    *n_out = s->n_rows;
     return 0;
 }
 
@@ -867,6 +918,7 @@ int isx_add(isx_store_t* s, const void* keys, const uint8_t* codes, const uint8_
     std::lock_guard<std::mutex> gw(s->work_mu);
     int rc = set_device(s);
     if (rc) return rc;
+    if ((rc = sync_map(s))) return rc;
     for (size_t i = 0; i < n; i++) {
         uint32_t L = lens[i];
         if (L < 1 || L > s->max_bytes) return fail(ISX_EINVAL, "row %zu: code length %u bytes outside 1..%u", i, L, s->max_bytes);
@@ -898,12 +950,14 @@ int isx_add(isx_store_t* s, const void* keys, const uint8_t* codes, const uint8_
         uint32_t sid = bs.back();
         Segment& sg = s->segs[sid];
         uint32_t row = sg.desc.n++;
+        sg.mirrored = sg.desc.n;
         sg.h_khi[row] = key.hi;
         if (s->key_bytes == 16) sg.h_klo[row] = key.lo;
         uint64_t loc = ((uint64_t)sid << 32) | row;
         s->map.insert(key, loc);
         dest[i] = loc;
         s->bucket_rows[L]++;
+        s->n_rows++;
         need[L]--;
         if (added) added[i] = 1;
         n_added++;
@@ -938,6 +992,7 @@ int isx_remove(isx_store_t* s, const void* keys, size_t n, uint8_t* removed, uin
     std::lock_guard<std::mutex> gw(s->work_mu);
     int rc = set_device(s);
     if (rc) return rc;
+    if ((rc = sync_map(s))) return rc;
     std::vector<uint4> moves;
     uint64_t cnt = 0;
     for (size_t i = 0; i < n; i++) {
@@ -963,7 +1018,9 @@ int isx_remove(isx_store_t* s, const void* keys, size_t n, uint8_t* removed, uin
             moves.push_back(make_uint4(sid, row, lsid, lrow));
         }
         last.desc.n--;
+        last.mirrored = last.desc.n;
         s->bucket_rows[L]--;
+        s->n_rows--;
         if (removed) removed[i] = 1;
         cnt++;
     }
@@ -982,10 +1039,132 @@ int isx_remove(isx_store_t* s, const void* keys, size_t n, uint8_t* removed, uin
     return 0;
 }
 
+// rows [i0, i0+cn) of a device batch -> free rows of their length buckets (caller holds both locks)
+static int add_device_chunk(isx_store* s, const uint8_t* d_keys, const uint8_t* d_codes, const uint8_t* d_lens, uint32_t uniform_len, size_t cn) {
+    int rc;
+    uint32_t counts[256] = {0};
+    if (s->d_bulk.ensure(256 * 4 + 64 * 4)) return ISX_ENOMEM;
+    uint32_t* d_hist = s->d_bulk.as<uint32_t>();
+    uint32_t* d_cursor = d_hist + 256;
+    CU(cudaMemsetAsync(d_hist, 0, (256 + 64) * 4, s->stream));
+    if (d_lens) {
+        k_len_hist<<<std::min<size_t>((cn + 4095) / 4096, (size_t)s->sm_count * 8), 256, 0, s->stream>>>(d_lens, cn, d_hist);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(counts, d_hist, sizeof counts, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    } else {
+        counts[uniform_len] = (uint32_t)cn;
+    }
+    for (uint32_t L = 0; L < 256; L++) {
+        if (!counts[L]) continue;
+        if (L < 1 || L > s->max_bytes) return fail(ISX_EINVAL, "isx_add_device: code length %u bytes outside 1..%u", L, s->max_bytes);
+        if (s->fixed_len && L != s->fixed_len) return fail(ISX_EINVAL, "isx_add_device: code length %u bytes, index expects %u", L, s->fixed_len);
+    }
+    // plan: spans of free rows per length class (tail of the bucket's last segment, then fresh segments); nothing is
+    // committed to the descriptors before the whole plan fits
+    struct Pending { uint32_t L, sid, row0, cnt; };
+    std::vector<Pending> pend;
+    std::vector<std::pair<uint32_t, uint32_t>> fresh;  // (L, cap) segments to create
+    BulkPlan plan{};
+    uint32_t n_spans = 0;
+    for (uint32_t L = 1; L <= kMaxBytes; L++) {
+        plan.span_lo[L] = n_spans;
+        uint64_t left = counts[L], first = 0;
+        if (!left) continue;
+        auto& bs = s->bucket_segs[L];
+        uint32_t last_cap = 0;
+        if (!bs.empty()) {
+            const SegDesc& d = s->segs[bs.back()].desc;
+            last_cap = d.cap;
+            if (d.n < d.cap) {
+                const uint32_t take = (uint32_t)std::min<uint64_t>(left, d.cap - d.n);
+                pend.push_back({L, bs.back(), d.n, take});
+                if (n_spans < kMaxBulkSpans) plan.spans[n_spans] = BulkSpan{bs.back(), d.n, (uint32_t)first, 0};
+                n_spans++; first += take; left -= take;
+            }
+        }
+        uint32_t next_sid = (uint32_t)(s->segs.size() + fresh.size());
+        while (left) {
+            const uint32_t grow = last_cap ? (uint32_t)std::min<uint64_t>((uint64_t)last_cap * 4, kMaxSegRows) : kMinSegRows;
+            const uint64_t want = std::max<uint64_t>(grow, std::min<uint64_t>(left, kMaxSegRows));
+            const uint32_t cap = (uint32_t)((want + kMinSegRows - 1) / kMinSegRows * kMinSegRows);
+            const uint32_t take = (uint32_t)std::min<uint64_t>(left, cap);
+            fresh.push_back({L, cap});
+            pend.push_back({L, next_sid, 0, take});
+            if (n_spans < kMaxBulkSpans) plan.spans[n_spans] = BulkSpan{next_sid, 0, (uint32_t)first, 0};
+            n_spans++; next_sid++; first += take; left -= take; last_cap = cap;
+        }
+    }
+    plan.span_lo[kMaxBytes + 1] = n_spans;
+    if (n_spans > kMaxBulkSpans) return ISX_ELIMIT;  // caller splits the chunk
+    for (auto& f : fresh)
+        if ((rc = new_segment(s, f.first, f.second, /*mirror=*/false))) return rc;
+    if ((rc = upload_segs(s))) return rc;  // plane / key pointers of the fresh segments (row counts still the old ones)
+    k_scatter_bulk<<<(unsigned)((cn + 255) / 256), 256, 0, s->stream>>>(s->d_segs.as<SegDesc>(), plan, d_cursor, d_keys, d_codes, d_lens,
+                                                                        uniform_len, s->key_bytes, cn);
+    CU(cudaGetLastError());
+    for (const Pending& pd : pend) {
+        s->segs[pd.sid].desc.n = pd.row0 + pd.cnt;
+        s->bucket_rows[pd.L] += pd.cnt;
+        s->n_rows += pd.cnt;
+    }
+    s->segs_dirty = true;
+    s->version++;
+    s->map_stale.store(true);
+    return 0;
+}
+
+int isx_add_device(isx_store_t* s, const void* d_keys, const uint8_t* d_codes, const uint8_t* d_lens, uint32_t uniform_len, size_t n) {
+    if (!s) return fail(ISX_EINVAL, "store is NULL");
+    if (n == 0) return 0;
+    if (!d_keys || !d_codes) return fail(ISX_EINVAL, "NULL input array");
+    if (!d_lens && (uniform_len < 1 || uniform_len > s->max_bytes || (s->fixed_len && uniform_len != s->fixed_len)))
+        return fail(ISX_EINVAL, "isx_add_device: uniform_len %u bytes not accepted by this index", uniform_len);
+    std::unique_lock<std::shared_mutex> g(s->rows_mu);
+    std::lock_guard<std::mutex> gw(s->work_mu);
+    int rc = set_device(s);
+    if (rc) return rc;
+    const uint8_t* keys = reinterpret_cast<const uint8_t*>(d_keys);
+    size_t chunk = (size_t)16 << 20;
+    for (size_t i0 = 0; i0 < n;) {
+        const size_t cn = std::min(chunk, n - i0);
+        rc = add_device_chunk(s, keys + i0 * s->key_bytes, d_codes + i0 * 32, d_lens ? d_lens + i0 : nullptr, uniform_len, cn);
+        if (rc == ISX_ELIMIT && chunk > 4096) { chunk /= 2; continue; }  // too many spans for one launch: smaller chunks
+        if (rc) return rc == ISX_ELIMIT ? fail(ISX_ELIMIT, "isx_add_device: cannot plan the append") : rc;
+        i0 += cn;
+    }
+    if ((rc = upload_segs(s))) return rc;
+    CU(cudaStreamSynchronize(s->stream));  // the caller may reuse its buffers when this returns
+    return 0;
+}
+
+int isx_synth_rows_device(isx_store_t* s, uint64_t seed, uint64_t start, size_t n, const uint8_t* lengths, uint32_t n_lengths,
+                          uint32_t key_mode, uint32_t chunks_per_asset, uint32_t dup_every, uint32_t dup_back, void* d_keys,
+                          uint8_t* d_codes, uint8_t* d_lens) {
+    if (!s) return fail(ISX_EINVAL, "store is NULL");
+    if (n == 0) return 0;
+    if (!lengths || n_lengths < 1 || n_lengths > 8 || !d_keys || !d_codes) return fail(ISX_EINVAL, "bad argument");
+    if (key_mode > 1 || (key_mode == 1 && chunks_per_asset < 1)) return fail(ISX_EINVAL, "bad key_mode / chunks_per_asset");
+    std::lock_guard<std::mutex> gw(s->work_mu);
+    int rc = set_device(s);
+    if (rc) return rc;
+    SynthParams g{};
+    g.seed = seed; g.start = start; g.n_lengths = n_lengths; g.key_mode = key_mode; g.cpa = chunks_per_asset;
+    g.dup_every = dup_every; g.dup_back = dup_back;
+    for (uint32_t i = 0; i < n_lengths; i++) {
+        if (lengths[i] < 1 || lengths[i] > kMaxBytes) return fail(ISX_EINVAL, "length %u outside 1..32", lengths[i]);
+        g.lengths[i] = lengths[i];
+    }
+    k_synth_rows<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(g, n, reinterpret_cast<uint8_t*>(d_keys), d_codes, d_lens);
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int isx_contains(isx_store_t* s, const void* keys, size_t n, uint8_t* present) {
     if (!s) return fail(ISX_EINVAL, "store is NULL");
     if (n == 0) return 0;
     if (!keys || !present) return fail(ISX_EINVAL, "NULL argument");
+    if (int rc0 = ensure_map(s)) return rc0;
     std::shared_lock<std::shared_mutex> g(s->rows_mu);
     for (size_t i = 0; i < n; i++) {
         uint64_t loc;
@@ -998,6 +1177,7 @@ int isx_get(isx_store_t* s, const void* keys, size_t n, uint8_t* codes_out, uint
     if (!s) return fail(ISX_EINVAL, "store is NULL");
     if (n == 0) return 0;
     if (!keys || !codes_out || !lens_out) return fail(ISX_EINVAL, "NULL argument");
+    if (int rc0 = ensure_map(s)) return rc0;
     std::shared_lock<std::shared_mutex> g(s->rows_mu);
     std::lock_guard<std::mutex> gw(s->work_mu);
     int rc = set_device(s);
@@ -1234,6 +1414,14 @@ int isx_share_reset(isx_store_t* s) {
     for (uint32_t r = 0; r < s->share_world; r++)
         if (!s->share_ptrs[r]) return fail(ISX_EINVAL, "peer %u is not attached", r);
     CU(cudaMemsetAsync(s->share_local, 0, s->share_bytes, s->stream));
+    s->share_armed = true;
+    return 0;
+}
+
+int isx_share_set_lengths(isx_store_t* s, uint32_t global_length_mask) {
+    if (!s) return fail(ISX_EINVAL, "store is NULL");
+    std::lock_guard<std::mutex> gw(s->work_mu);
+    s->share_len_mask = global_length_mask;
     return 0;
 }
 
@@ -1351,6 +1539,7 @@ static const char kMagic[8] = {'I', 'S', 'X', 'B', '2', '0', '0', '1'};
 
 int isx_save(isx_store_t* s, const char* path) {
     if (!s || !path) return fail(ISX_EINVAL, "NULL argument");
+    if (int rc0 = ensure_map(s)) return rc0;
     std::shared_lock<std::shared_mutex> g(s->rows_mu);
     std::lock_guard<std::mutex> gw(s->work_mu);
     int rc = set_device(s);
@@ -1361,7 +1550,7 @@ int isx_save(isx_store_t* s, const char* path) {
     bool ok = true;
     auto W = [&](const void* p, size_t n) { if (ok && n && fwrite(p, 1, n, f) != n) ok = false; };
     uint32_t hdr[4] = {s->key_bytes, s->max_bytes, s->fixed_len, 0};
-    uint64_t total = s->map.size();
+    uint64_t total = s->n_rows;
     W(kMagic, 8); W(hdr, sizeof hdr); W(&total, 8);
     std::vector<uint32_t> plane;
     std::vector<uint8_t> rows;

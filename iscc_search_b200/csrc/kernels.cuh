@@ -854,6 +854,111 @@ __global__ void k_scatter_rows(const SegDesc* segs, const uint64_t* dest, const 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Bulk append from DEVICE memory (isx_add_device): rows of one length class go to consecutive free rows, described
+// by a few spans (tail of the last segment + fresh segments). Row i takes the next index of its class (mixed lengths:
+// one warp-aggregated atomic per class and warp; uniform length: the index is i itself).
+struct BulkSpan { uint32_t seg, row0, first, pad; };  // class-relative rows [first, next span's first) -> seg rows row0..
+constexpr int kMaxBulkSpans = 96;
+struct BulkPlan {
+    uint32_t span_lo[kMaxBytes + 2];  // spans of length class L: [span_lo[L], span_lo[L+1])
+    BulkSpan spans[kMaxBulkSpans];
+};
+
+__global__ void k_len_hist(const uint8_t* __restrict__ lens, size_t n, uint32_t* __restrict__ hist /*256*/) {
+    __shared__ uint32_t sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) atomicAdd(&sh[lens[i]], 1u);
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+__global__ void k_scatter_bulk(const SegDesc* segs, const __grid_constant__ BulkPlan plan, uint32_t* cursor /*[33]*/, const uint8_t* keys,
+                               const uint8_t* codes, const uint8_t* lens, uint32_t uniform_len, uint32_t key_bytes, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t L = lens ? lens[i] : uniform_len;
+    uint32_t idx;
+    if (lens) {
+        const unsigned grp = __match_any_sync(__activemask(), L);
+        const int leader = __ffs(grp) - 1;
+        const uint32_t lane = threadIdx.x & 31;
+        uint32_t base = 0;
+        if ((int)lane == leader) base = atomicAdd(&cursor[L], (uint32_t)__popc(grp));
+        base = __shfl_sync(grp, base, leader);
+        idx = base + __popc(grp & ((1u << lane) - 1u));
+    } else {
+        idx = (uint32_t)i;
+    }
+    uint32_t sp = plan.span_lo[L + 1] - 1;
+    while (sp > plan.span_lo[L] && plan.spans[sp].first > idx) sp--;
+    const BulkSpan span = plan.spans[sp];
+    const SegDesc sd = segs[span.seg];
+    const uint32_t row = span.row0 + (idx - span.first);
+    const uint32_t* c = reinterpret_cast<const uint32_t*>(codes + i * kMaxBytes);
+    for (uint32_t w = 0; w < sd.words; w++) {
+        uint32_t v = c[w];
+        if (4 * w + 4 > L) v &= (1u << (8 * (L - 4 * w))) - 1u;  // bytes beyond the code's length are never stored
+        sd.planes[(size_t)w * sd.cap + row] = v;
+    }
+    if (key_bytes == 8) {
+        sd.khi[row] = reinterpret_cast<const uint64_t*>(keys)[i];
+    } else {
+        const uint8_t* kb = keys + i * 16;
+        uint64_t hi = 0, lo = 0;
+        for (int b = 0; b < 8; b++) { hi = (hi << 8) | kb[b]; lo = (lo << 8) | kb[8 + b]; }
+        sd.khi[row] = hi; sd.klo[row] = lo;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Synthetic rows of SURVEY.md 8d on the device (definition: iscc_search_b200/synth.py; the CPU checker regenerates
+// the same rows): word w of row i = splitmix64(seed ^ (4i + w)), length = lengths[mix(i) % n_lengths], key = bijective
+// mix of i (key_mode 0, uint64) or the chunk pointer asset8|offset4|size4 as 16 big-endian bytes (key_mode 1).
+// 1 B rows never cross PCIe: they are generated next to the store and appended with isx_add_device.
+struct SynthParams {
+    uint64_t seed, start;
+    uint8_t lengths[8];
+    uint32_t n_lengths, key_mode, cpa, dup_every, dup_back;
+};
+__device__ __forceinline__ uint64_t splitmix64_dev(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void k_synth_rows(const __grid_constant__ SynthParams g, size_t n, uint8_t* keys, uint8_t* codes, uint8_t* lens) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint64_t i = g.start + j;
+    const uint32_t L = g.lengths[g.n_lengths > 1 ? (uint32_t)(splitmix64_dev(i ^ (g.seed + 0x1234567ull)) % g.n_lengths) : 0u];
+    const uint64_t src = (g.dup_every && i % g.dup_every == g.dup_every - 1 && i >= g.dup_back) ? i - g.dup_back : i;
+    uint64_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint64_t v = splitmix64_dev(g.seed ^ (src * 4 + k));
+        const uint32_t lo = 8u * k;
+        if (L <= lo) v = 0;
+        else if (L < lo + 8) v &= (1ull << (8 * (L - lo))) - 1ull;
+        w[k] = v;
+    }
+    uint4* c = reinterpret_cast<uint4*>(codes + j * kMaxBytes);
+    c[0] = make_uint4((uint32_t)w[0], (uint32_t)(w[0] >> 32), (uint32_t)w[1], (uint32_t)(w[1] >> 32));
+    c[1] = make_uint4((uint32_t)w[2], (uint32_t)(w[2] >> 32), (uint32_t)w[3], (uint32_t)(w[3] >> 32));
+    if (lens) lens[j] = (uint8_t)L;
+    const uint64_t kc = g.seed * 0x51ED27ull + 0xA5A5A5A5ull;
+    if (g.key_mode == 0) {
+        reinterpret_cast<uint64_t*>(keys)[j] = splitmix64_dev(i ^ kc);
+    } else {
+        const uint64_t hi = splitmix64_dev((i / g.cpa) ^ kc);
+        const uint64_t lo = ((uint64_t)((uint32_t)(i % g.cpa) * 4096u) << 32) | 4096u;
+        uint8_t* kb = keys + j * 16;
+#pragma unroll
+        for (int b = 0; b < 8; b++) { kb[b] = (uint8_t)(hi >> (56 - 8 * b)); kb[8 + b] = (uint8_t)(lo >> (56 - 8 * b)); }
+    }
+}
+
 // Ordered row moves of swap-remove: move[i] = (dst seg, dst row, src seg, src row); one warp walks
 // the list in order (moves may chain), lane w copies word w.
 __global__ void k_move_rows(const SegDesc* segs, const uint4* moves, size_t n) {

@@ -38,10 +38,39 @@ def make_lengths(start, n, seed=0, lengths=STANDARD_LENGTHS):
     return np.asarray(lengths, dtype=np.uint8)[(r % _U(len(lengths))).astype(np.int64)]
 
 
-def make_codes(start, n, seed=0, lens=None):
-    # type: (int, int, int, np.ndarray|None) -> np.ndarray
-    """uint8[n, 32] codes, zero padded beyond each row's length (all 32 bytes if `lens` is None)."""
+def make_keys128(start, n, seed=0, chunks_per_asset=64):
+    # type: (int, int, int, int) -> tuple[np.ndarray, np.ndarray]
+    """
+    Simprint chunk pointers `asset8 | offset4 | size4` (lmdb_ops.py:30-49) as (hi, lo) uint64 halves of the big-endian
+    16-byte key: row i is chunk `i % chunks_per_asset` of asset `i // chunks_per_asset`; asset ids are a bijective mix
+    (unique, unsorted), offsets are multiples of 4096, size 4096.
+    """
     i = np.arange(start, start + n, dtype=_U)
+    cpa = _U(chunks_per_asset)
+    hi = splitmix64((i // cpa) ^ _U((seed * 0x51ED27 + 0xA5A5A5A5) & 0xFFFFFFFFFFFFFFFF))
+    lo = (((i % cpa) * _U(4096)) << _U(32)) | _U(4096)
+    return hi, lo
+
+
+def keys128_bytes(hi, lo):
+    # type: (np.ndarray, np.ndarray) -> np.ndarray
+    """(hi, lo) halves -> uint8[n, 16] big-endian rows, the form 16-byte keys cross the C ABI in."""
+    out = np.empty((len(hi), 16), dtype=np.uint8)
+    out[:, :8] = np.asarray(hi, dtype=_U).astype(">u8").view(np.uint8).reshape(-1, 8)
+    out[:, 8:] = np.asarray(lo, dtype=_U).astype(">u8").view(np.uint8).reshape(-1, 8)
+    return out
+
+
+def make_codes(start, n, seed=0, lens=None, dup_every=0, dup_back=0):
+    # type: (int, int, int, np.ndarray|None, int, int) -> np.ndarray
+    """
+    uint8[n, 32] codes, zero padded beyond each row's length (all 32 bytes if `lens` is None).
+    `dup_every` > 0: row i with i % dup_every == dup_every - 1 (and i >= dup_back) repeats the words of row
+    i - dup_back, so exact duplicates exist (chunks shared between assets, for the simprint equality join).
+    """
+    i = np.arange(start, start + n, dtype=_U)
+    if dup_every:
+        i = np.where((i % _U(dup_every) == _U(dup_every - 1)) & (i >= _U(dup_back)), i - _U(dup_back), i)
     words = np.empty((n, 4), dtype=_U)
     for w in range(4):
         words[:, w] = splitmix64(_U(seed) ^ (i * _U(4) + _U(w)))

@@ -34,6 +34,12 @@ def lib():
         L.oracle_nphd_topk.argtypes = [u8p, u8p, u64p, u64p, ctypes.c_size_t, u8p, u8p, ctypes.c_size_t, ctypes.c_uint32,
                                        ctypes.c_uint32, ctypes.c_uint32, i64p, u16p, u16p, u32p, ctypes.c_int]
         L.oracle_num_threads.restype = ctypes.c_int
+        u32, u64 = ctypes.c_uint32, ctypes.c_uint64
+        L.oracle_synth_rows.restype = ctypes.c_int
+        L.oracle_synth_rows.argtypes = [u64, u64, ctypes.c_size_t, u8p, u32, u32, u32, u32, u32, u64p, u64p, u8p, u8p, ctypes.c_int]
+        L.oracle_synth_topk.restype = ctypes.c_int
+        L.oracle_synth_topk.argtypes = [u64, u64, u8p, u32, u32, u32, u32, u32, u8p, u8p, ctypes.c_size_t, u32, u32, u32,
+                                        u64p, u64p, u16p, u16p, u32p, ctypes.c_int]
         _lib = L
     return _lib
 
@@ -71,6 +77,50 @@ def topk(keys_hi, keys_lo, codes, lens, queries, qlens, k, max_h_over_n=None, n_
     if rc != 0:
         raise ValueError("oracle_nphd_topk: bad arguments")
     return rows, h, nb, counts
+
+
+def synth_rows(start, n, seed, lengths=(8, 16, 24, 32), key_mode=0, cpa=64, dup_every=0, dup_back=0, n_threads=0):
+    # type: (...) -> tuple[np.ndarray, np.ndarray|None, np.ndarray, np.ndarray]
+    """C copy of iscc_search_b200.synth (make_keys / make_keys128, make_lengths, make_codes): -> (khi, klo|None, codes, lens)."""
+    lengths = np.ascontiguousarray(lengths, dtype=np.uint8)
+    khi = np.empty(n, dtype=np.uint64)
+    klo = np.empty(n, dtype=np.uint64) if key_mode else None
+    codes = np.empty((n, 32), dtype=np.uint8)
+    lens = np.empty(n, dtype=np.uint8)
+    rc = lib().oracle_synth_rows(seed, start, n, _p(lengths, ctypes.c_uint8), len(lengths), key_mode, cpa, dup_every, dup_back,
+                                 _p(khi, ctypes.c_uint64), _p(klo, ctypes.c_uint64), _p(codes, ctypes.c_uint8),
+                                 _p(lens, ctypes.c_uint8), n_threads)
+    if rc != 0:
+        raise ValueError("oracle_synth_rows: bad arguments")
+    return khi, klo, codes, lens
+
+
+def synth_topk(n_rows, seed, queries, qlens, k, lengths=(8, 16, 24, 32), key_mode=0, cpa=64, dup_every=0, dup_back=0,
+               max_h_over_n=None, n_threads=0):
+    # type: (...) -> tuple[np.ndarray, np.ndarray|None, np.ndarray, np.ndarray, np.ndarray]
+    """
+    Exact top-k over `n_rows` synthetic rows regenerated block by block (nothing materialised: works at 1 B rows).
+    -> (keys_hi uint64[Q,k], keys_lo|None, h, nbits, counts); unused slots: key = 2**64-1, h = nbits = 0.
+    """
+    if k < 1:
+        raise ValueError("`count` must be >= 1")
+    lengths = np.ascontiguousarray(lengths, dtype=np.uint8)
+    queries = np.ascontiguousarray(queries, dtype=np.uint8)
+    qlens = np.ascontiguousarray(qlens, dtype=np.uint8)
+    q = len(qlens)
+    khi = np.empty((q, k), dtype=np.uint64)
+    klo = np.empty((q, k), dtype=np.uint64) if key_mode else None
+    h = np.empty((q, k), dtype=np.uint16)
+    nb = np.empty((q, k), dtype=np.uint16)
+    counts = np.empty(q, dtype=np.uint32)
+    tn, td = (0, 0) if max_h_over_n is None else max_h_over_n
+    rc = lib().oracle_synth_topk(seed, n_rows, _p(lengths, ctypes.c_uint8), len(lengths), key_mode, cpa, dup_every, dup_back,
+                                 _p(queries, ctypes.c_uint8), _p(qlens, ctypes.c_uint8), q, k, tn, td, _p(khi, ctypes.c_uint64),
+                                 _p(klo, ctypes.c_uint64), _p(h, ctypes.c_uint16), _p(nb, ctypes.c_uint16),
+                                 _p(counts, ctypes.c_uint32), n_threads)
+    if rc != 0:
+        raise ValueError("oracle_synth_topk: bad arguments")
+    return khi, klo, h, nb, counts
 
 
 def num_threads():

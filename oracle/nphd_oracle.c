@@ -147,6 +147,153 @@ int oracle_nphd_topk(const uint8_t* codes, const uint8_t* lens, const uint64_t* 
     return bad ? -1 : 0;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Synthetic rows of SURVEY.md 8d, restating iscc_search_b200/synth.py (the definition; tests/test_oracle.py
+ * checks this C copy against it): row i, 64-bit word w = splitmix64(seed ^ (4i + w)); length = lengths[mix(i) % n];
+ * key = bijective mix of i (key_mode 0) or the simprint chunk pointer asset8 | offset4 | size4 of chunk i % cpa of
+ * asset i / cpa (key_mode 1, lmdb_ops.py:30-49). dup_every > 0: row i with i % dup_every == dup_every - 1 repeats
+ * the code of row i - dup_back (shared chunks -> exact duplicates exist for the equality join).
+ * Lets the checker cover stores that do not fit host memory (1 B rows): rows are regenerated block by block.
+ */
+static inline uint64_t splitmix64(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+typedef struct {
+    uint64_t seed;
+    const uint8_t* lengths;
+    uint32_t n_lengths, key_mode, cpa, dup_every, dup_back;
+} synth_t;
+
+static inline void synth_row(const synth_t* g, uint64_t i, uint8_t* code /*32*/, uint8_t* len, uint64_t* khi, uint64_t* klo) {
+    uint32_t L = g->lengths[g->n_lengths > 1 ? splitmix64(i ^ ((g->seed + 0x1234567ull))) % g->n_lengths : 0];
+    uint64_t src = (g->dup_every && i % g->dup_every == g->dup_every - 1 && i >= g->dup_back) ? i - g->dup_back : i;
+    uint64_t w[4];
+    for (uint32_t k = 0; k < 4; k++) w[k] = splitmix64(g->seed ^ (src * 4 + k));
+    memcpy(code, w, 32);
+    memset(code + L, 0, 32 - L);
+    *len = (uint8_t)L;
+    const uint64_t kc = (g->seed * 0x51ED27ull + 0xA5A5A5A5ull);
+    if (g->key_mode == 0) { *khi = splitmix64(i ^ kc); *klo = 0; }
+    else { *khi = splitmix64((i / g->cpa) ^ kc); *klo = ((uint64_t)((i % g->cpa) * 4096u) << 32) | 4096u; }
+}
+
+int oracle_synth_rows(uint64_t seed, uint64_t start, size_t n, const uint8_t* lengths, uint32_t n_lengths, uint32_t key_mode,
+                      uint32_t cpa, uint32_t dup_every, uint32_t dup_back, uint64_t* keys_hi, uint64_t* keys_lo, uint8_t* codes,
+                      uint8_t* lens, int n_threads) {
+    if (!lengths || n_lengths < 1 || (key_mode == 1 && cpa < 1)) return -1;
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+    synth_t g = {seed, lengths, n_lengths, key_mode, cpa, dup_every, dup_back};
+#pragma omp parallel for schedule(static)
+    for (long j = 0; j < (long)n; j++) {
+        uint64_t hi, lo;
+        synth_row(&g, start + (uint64_t)j, codes + (size_t)j * MAXB, lens + j, &hi, &lo);
+        keys_hi[j] = hi;
+        if (keys_lo) keys_lo[j] = lo;
+    }
+    return 0;
+}
+
+/* Exact top-k over n_rows synthetic rows WITHOUT materialising them: threads take blocks of rows, regenerate them,
+ * score every query against the block and keep one bounded heap per (thread, query); the heaps are merged at the end.
+ * Same order and threshold rules as oracle_nphd_topk. Outputs: keys (hi, lo), h, nbits, counts. */
+int oracle_synth_topk(uint64_t seed, uint64_t n_rows, const uint8_t* lengths, uint32_t n_lengths, uint32_t key_mode, uint32_t cpa,
+                      uint32_t dup_every, uint32_t dup_back, const uint8_t* queries, const uint8_t* qlens, size_t q, uint32_t k,
+                      uint32_t thr_num, uint32_t thr_den, uint64_t* out_khi, uint64_t* out_klo, uint16_t* out_h, uint16_t* out_n,
+                      uint32_t* counts, int n_threads) {
+    if (k < 1 || !lengths || n_lengths < 1 || (key_mode == 1 && cpa < 1)) return -1;
+    for (size_t i = 0; i < q; i++) if (qlens[i] < 1 || qlens[i] > MAXB) return -1;
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+    const int T = omp_get_max_threads();
+#else
+    const int T = 1;
+#endif
+    if (!g_mask_ready) init_masks();
+    synth_t g = {seed, lengths, n_lengths, key_mode, cpa, dup_every, dup_back};
+    enum { BLK = 2048 };
+    cand_t* heaps = (cand_t*)malloc(sizeof(cand_t) * (size_t)T * q * k);
+    size_t* cnts = (size_t*)calloc((size_t)T * q, sizeof(size_t));
+    uint64_t* worst = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)T * q);
+    if (!heaps || !cnts || !worst) { free(heaps); free(cnts); free(worst); return -1; }
+    for (size_t i = 0; i < (size_t)T * q; i++) worst[i] = UINT64_MAX;
+    uint64_t scale[MAXB + 1];
+    scale[0] = 0;
+    for (uint32_t m = 1; m <= MAXB; m++) scale[m] = LCM_BITS / (8ull * m);
+    const long n_blocks = (long)((n_rows + BLK - 1) / BLK);
+#pragma omp parallel
+    {
+#ifdef _OPENMP
+        const int t = omp_get_thread_num();
+#else
+        const int t = 0;
+#endif
+        uint8_t* codes = (uint8_t*)malloc((size_t)BLK * MAXB);
+        uint8_t lens[BLK];
+        uint64_t khi[BLK], klo[BLK];
+#pragma omp for schedule(dynamic, 4)
+        for (long b = 0; b < n_blocks; b++) {
+            const uint64_t r0 = (uint64_t)b * BLK;
+            const uint32_t bn = (uint32_t)((n_rows - r0 < BLK) ? n_rows - r0 : BLK);
+            for (uint32_t j = 0; j < bn; j++) synth_row(&g, r0 + j, codes + (size_t)j * MAXB, lens + j, khi + j, klo + j);
+            for (size_t qi = 0; qi < q; qi++) {
+                const uint32_t ql = qlens[qi];
+                uint64_t qw[4];
+                for (int w = 0; w < 4; w++) qw[w] = load64(queries + qi * MAXB + 8 * w);
+                cand_t* hp = heaps + ((size_t)t * q + qi) * k;
+                size_t cnt = cnts[(size_t)t * q + qi];
+                uint64_t wst = worst[(size_t)t * q + qi];
+                for (uint32_t j = 0; j < bn; j++) {
+                    const uint32_t m = lens[j] < ql ? lens[j] : ql;
+                    const uint32_t h = prefix_hamming(codes + (size_t)j * MAXB, qw, m);
+                    const uint64_t dnum = (uint64_t)h * scale[m];
+                    if (dnum > wst) continue;
+                    if (thr_den && (uint64_t)h * thr_den > (uint64_t)thr_num * 8ull * m) continue;
+                    cand_t c; c.dnum = dnum; c.khi = khi[j]; c.klo = klo[j]; c.row = 0; c.h = (uint16_t)h; c.n = (uint16_t)(8 * m);
+                    if (cnt < k) {
+                        hp[cnt] = c; heap_sift_up(hp, cnt); cnt++;
+                        if (cnt == k) wst = hp[0].dnum;
+                    } else if (cand_less(&c, &hp[0])) {
+                        hp[0] = c; heap_sift_down(hp, cnt, 0); wst = hp[0].dnum;
+                    }
+                }
+                cnts[(size_t)t * q + qi] = cnt;
+                worst[(size_t)t * q + qi] = wst;
+            }
+        }
+        free(codes);
+    }
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long qi = 0; qi < (long)q; qi++) {
+        size_t total = 0;
+        for (int t = 0; t < T; t++) total += cnts[(size_t)t * q + qi];
+        cand_t* all = (cand_t*)malloc(sizeof(cand_t) * (total ? total : 1));
+        if (!all) { bad = 1; counts[qi] = 0; continue; }
+        size_t o = 0;
+        for (int t = 0; t < T; t++) {
+            memcpy(all + o, heaps + ((size_t)t * q + qi) * k, sizeof(cand_t) * cnts[(size_t)t * q + qi]);
+            o += cnts[(size_t)t * q + qi];
+        }
+        qsort(all, total, sizeof(cand_t), cand_cmp_qsort);
+        const size_t c = total < k ? total : k;
+        for (size_t j = 0; j < k; j++) {
+            const size_t oo = (size_t)qi * k + j;
+            if (j < c) { out_khi[oo] = all[j].khi; if (out_klo) out_klo[oo] = all[j].klo; out_h[oo] = all[j].h; out_n[oo] = all[j].n; }
+            else { out_khi[oo] = ~0ull; if (out_klo) out_klo[oo] = ~0ull; out_h[oo] = 0; out_n[oo] = 0; }
+        }
+        counts[qi] = (uint32_t)c;
+        free(all);
+    }
+    free(heaps); free(cnts); free(worst);
+    return bad ? -1 : 0;
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -52,6 +52,22 @@ if args.backend == "nccl":
     fb = st.stats()["fallback_queries"]
     if rank == 0:
         np.savez(args.out.replace(".npz", "_dup.npz"), keys=gk3, h=gh3, nb=gn3, cnt=gc3, fallback=fb, dup_n=dup_n)
+    # fourth batch, fresh stores whose shards hold DIFFERENT length buckets (192-bit rows only on rank 0, 128-bit rows
+    # only on the last rank): the rank tables must still agree across ranks (global class mask), else the shared
+    # histograms are indexed inconsistently and true neighbours are dropped
+    st4 = _lib.Store(device=rank, key_bytes=8, max_bytes=32)
+    own = owner_of(keys, world)
+    own[lens == 24] = 0
+    own[lens == 16] = world - 1
+    sel4 = own == rank
+    st4.add(np.ascontiguousarray(keys[sel4]), np.ascontiguousarray(codes[sel4]), np.ascontiguousarray(lens[sel4]))
+    masks = [None] * world
+    dist.all_gather_object(masks, st4.length_mask())
+    s4 = ShardedSearcher(st4, rank, world, None, torch.device("cuda", rank))
+    gk4, gh4, gn4, gc4 = (a.copy() for a in s4.search(queries, qlens, k))
+    if rank == 0:
+        np.savez(args.out.replace(".npz", "_skew.npz"), keys=gk4, h=gh4, nb=gn4, cnt=gc4, masks=np.array(masks, dtype=np.int64),
+                 shared=s4.shared)
     if rank == 0:
         np.savez(args.out, keys=gk, h=gh, nb=gn, cnt=gc, keys2=gk2[inv], h2=gh2[inv], nb2=gn2[inv], cnt2=gc2[inv], n=n, q=q, k=k,
                  shared=searcher.shared)
@@ -71,7 +87,15 @@ else:
     raw[off["cnt"]: off["cnt"] + q * 4].view(np.uint32)[:] = k - rank
     gathered = torch.zeros(size * world, dtype=torch.uint8)
     dist.all_gather_into_tensor(gathered, local)
+    # stored-length masks differ per rank (rank r holds codes of 8*(r+1) bytes, rank 0 also 5-byte codes): every rank
+    # must come out with the union
+    from iscc_search_b200.sharded import global_length_mask
+
+    local_mask = (1 << (8 * (rank + 1) - 1)) | ((1 << 4) if rank == 0 else 0)
+    gmask = global_length_mask(local_mask, dist)
+    all_masks = [None] * world
+    dist.all_gather_object(all_masks, gmask)
     if rank == 0:
-        np.savez(args.out, gathered=gathered.numpy(), size=size, world=world, q=q, k=k)
+        np.savez(args.out, gathered=gathered.numpy(), size=size, world=world, q=q, k=k, gmasks=np.array(all_masks, dtype=np.int64))
     dist.barrier()
     dist.destroy_process_group()

@@ -141,3 +141,8 @@ def test_multi_rank_nccl_search_with_shared_thresholds_equals_oracle(cuda, tmp_p
     ql3 = np.concatenate([np.array([16], dtype=np.uint8), qlens[:7]])
     rows3, h3, nb3, cnt3 = oracle_topk(all_keys, all_codes, all_lens, q3, ql3, k)
     assert_same_topk(dd["keys"], dd["h"], dd["nb"], dd["cnt"], all_keys, rows3, h3, nb3, cnt3)
+    # fourth batch: shards with different length buckets (rank tables must come from the global class mask)
+    ds = np.load(str(out).replace(".npz", "_skew.npz"))
+    assert bool(ds["shared"])
+    assert len(set(ds["masks"].tolist())) > 1, "the shards were meant to hold different length buckets"
+    assert_same_topk(ds["keys"], ds["h"], ds["nb"], ds["cnt"], keys, rows, h, nb, cnt)

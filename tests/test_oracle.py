@@ -120,3 +120,46 @@ def test_synth_is_deterministic_and_row_addressable():
     lens = synth.make_lengths(0, 40_000, 9)
     assert set(np.unique(lens)) == set(synth.STANDARD_LENGTHS)
     assert np.all(synth.make_codes(0, 100, 9, lens[:100])[np.arange(32)[None, :] >= lens[:100, None]] == 0)
+
+
+def test_c_synth_generator_equals_the_python_definition():
+    """oracle_synth_rows restates iscc_search_b200/synth.py (the definition of the SURVEY 8d data set)."""
+    for start, n, seed in ((0, 5000, 1), (123_456_789, 3000, 7), (999_999_000, 1000, 4)):
+        khi, klo, codes, lens = c_oracle.synth_rows(start, n, seed)
+        assert klo is None
+        want_lens = synth.make_lengths(start, n, seed)
+        assert np.array_equal(lens, want_lens)
+        assert np.array_equal(codes, synth.make_codes(start, n, seed, want_lens))
+        assert np.array_equal(khi, synth.make_keys(start, n, seed))
+    # simprint flavour: fixed 8-byte codes, chunk-pointer keys, duplicated chunks
+    khi, klo, codes, lens = c_oracle.synth_rows(100, 4000, 4, lengths=(8,), key_mode=1, cpa=64, dup_every=16, dup_back=65)
+    l8 = np.full(4000, 8, dtype=np.uint8)
+    assert np.array_equal(lens, l8)
+    assert np.array_equal(codes, synth.make_codes(100, 4000, 4, l8, dup_every=16, dup_back=65))
+    hi, lo = synth.make_keys128(100, 4000, 4, 64)
+    assert np.array_equal(khi, hi) and np.array_equal(klo, lo)
+    assert (codes[111 - 100] == synth.make_codes(111 - 65, 1, 4, l8[:1])[0]).all()  # row 111 repeats row 46
+    kb = synth.keys128_bytes(hi, lo)
+    assert int.from_bytes(bytes(kb[5, :8]), "big") == int(hi[5]) and int.from_bytes(bytes(kb[5, 8:12]), "big") == ((105 % 64) * 4096)
+
+
+def test_streaming_synth_topk_equals_in_memory_oracle():
+    n, q, k = 70_000, 24, 50
+    khi, _, codes, lens = c_oracle.synth_rows(0, n, 3)
+    queries, qlens = synth.make_queries(q, n, 5, 3)
+    rows, h, nb, cnt = c_oracle.topk(khi, None, codes, lens, queries, qlens, k)
+    skhi, _, sh, snb, scnt = c_oracle.synth_topk(n, 3, queries, qlens, k, n_threads=3)
+    assert np.array_equal(scnt, cnt)
+    assert np.array_equal(skhi, khi[rows]) and np.array_equal(sh, h) and np.array_equal(snb, nb)
+    # threshold + 128-bit keys + duplicates, fewer matches than k
+    khi, klo, codes, lens = c_oracle.synth_rows(0, 30_000, 4, lengths=(8,), key_mode=1, dup_every=16, dup_back=65)
+    qs = codes[[14, 206, 4110]].copy()  # each is repeated 65 rows later
+    ql = np.full(3, 8, dtype=np.uint8)
+    rows, h, nb, cnt = c_oracle.topk(khi, klo, codes, lens, qs, ql, 40, (0, 64))
+    skhi, sklo, sh, snb, scnt = c_oracle.synth_topk(30_000, 4, qs, ql, 40, lengths=(8,), key_mode=1, dup_every=16, dup_back=65,
+                                                    max_h_over_n=(0, 64), n_threads=2)
+    assert np.array_equal(scnt, cnt) and (cnt >= 2).all()
+    for i in range(3):
+        c = int(cnt[i])
+        assert np.array_equal(skhi[i, :c], khi[rows[i, :c]]) and np.array_equal(sklo[i, :c], klo[rows[i, :c]])
+        assert np.array_equal(sh[i, :c], h[i, :c])

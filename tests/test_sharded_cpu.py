@@ -49,3 +49,6 @@ def test_gloo_world2_all_gather_delivers_rank_major_packed_buffers(tmp_path):
         assert np.array_equal(khi, np.arange(q * k, dtype=np.uint64) * 10 + rank)
         assert (raw[off["h"]: off["h"] + q * k * 2].view(np.uint16) == rank + 1).all()
         assert (raw[off["cnt"]: off["cnt"] + q * 4].view(np.uint32) == k - rank).all()
+    # the length-mask union every rank derives before a search with shared thresholds (same on all ranks)
+    want = (1 << 7) | (1 << 15) | (1 << 4)
+    assert d["gmasks"].tolist() == [want] * world
