@@ -58,7 +58,7 @@ SYMBOLS = (
 def build(force=False):
     # type: (bool) -> Path
     """Compile csrc/ for sm_100a with nvcc (in-tree, so the .so ships with the repo snapshot)."""
-    srcs = [CSRC / "isx.cu", CSRC / "kernels.cuh", CSRC / "keymap.hpp", _PKG.parent / "include" / "isx.h"]
+    srcs = [CSRC / "isx.cu", CSRC / "kernels.cuh", CSRC / "small.cuh", CSRC / "keymap.hpp", _PKG.parent / "include" / "isx.h"]
     stale = not SO_PATH.exists() or any(p.stat().st_mtime > SO_PATH.stat().st_mtime for p in srcs)
     if force or stale:
         r = subprocess.run(["make", "-C", str(CSRC)], capture_output=True, text=True)

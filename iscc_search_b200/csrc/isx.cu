@@ -19,6 +19,7 @@
 #include "../../include/isx.h"
 #include "kernels.cuh"
 #include "keymap.hpp"
+#include "small.cuh"
 
 namespace isx {
 
@@ -139,7 +140,7 @@ struct isx_store {
     // device mirrors
     DevBuf d_segs;
     bool segs_dirty = true;
-    DevBuf d_blocks;
+    DevBuf d_blocks, d_bdesc;
     uint64_t blocks_version = ~0ull;
     std::vector<uint2> h_blocks;
     uint32_t bucket_block_lo[kMaxBytes + 2] = {0};  // block range of bucket L: [lo[L], lo[L+1])
@@ -161,6 +162,16 @@ struct isx_store {
     DevBuf d_queries, d_tau, d_hist, d_shist, d_cnt, d_ovf, d_cand, d_qmap, d_fb, d_fb_cand;
     DevBuf d_out_khi, d_out_klo, d_out_h, d_out_n, d_out_cnt, d_out_codes, d_bigsort;
     PinnedBuf h_queries, h_qmap, h_flags, h_out;
+    // small-batch path (k_scan_small): per-query state kept clean between searches, results land in mapped pinned memory
+    DevBuf d_small;                 // tau[8] | cnt[8] | ovf[8] | hist[8][R] | shist[8][R]
+    uint32_t small_R = 0;           // R the state was laid out (and zeroed) for
+    PinnedBuf h_small_info;         // [8][4] status words written by the kernel
+    PinnedBuf h_small_dbg;
+    bool small_ok = true;           // cooperative launch available
+    // isx_search (host results): the fused select writes straight into the pinned result block (no D2H copies)
+    uint64_t* small_host_khi = nullptr; uint64_t* small_host_klo = nullptr; uint16_t* small_host_h = nullptr;
+    uint16_t* small_host_n = nullptr; uint32_t* small_host_cnt = nullptr;
+    bool small_host_valid = false, small_host_used = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> tile_events;  // 3 per tile, grown on demand (profiling only)
     isx_stats_t stats{};
@@ -242,9 +253,15 @@ static int upload_blocks(isx_store* s) {
     }
     s->bucket_block_lo[kMaxBytes + 1] = (uint32_t)s->h_blocks.size();
     size_t bytes = std::max<size_t>(s->h_blocks.size(), 1) * sizeof(uint2);
-    if (s->d_blocks.ensure(bytes)) return ISX_ECUDA;
+    if (s->d_blocks.ensure(bytes) || s->d_bdesc.ensure(std::max<size_t>(s->h_blocks.size(), 1) * sizeof(BlockDesc))) return ISX_ECUDA;
     if (!s->h_blocks.empty()) {
+        std::vector<BlockDesc> bd(s->h_blocks.size());
+        for (size_t i = 0; i < bd.size(); i++) {
+            const SegDesc& d = s->segs[s->h_blocks[i].x].desc;
+            bd[i] = BlockDesc{d.planes + s->h_blocks[i].y, d.cap, s->h_blocks[i].x, s->h_blocks[i].y, d.n, {0, 0}};
+        }
         CU(cudaMemcpyAsync(s->d_blocks.p, s->h_blocks.data(), s->h_blocks.size() * sizeof(uint2), cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(s->d_bdesc.p, bd.data(), bd.size() * sizeof(BlockDesc), cudaMemcpyHostToDevice, s->stream));
         CU(cudaStreamSynchronize(s->stream));
     }
     s->blocks_version = s->version;
@@ -453,6 +470,155 @@ struct SearchOut {
     uint64_t* khi; uint64_t* klo; uint16_t* h; uint16_t* n; uint32_t* cnt; uint8_t* codes;
 };
 
+// ---- small-batch path: the whole search in one cooperative launch (small.cuh) --------------------------------
+// Returns 0 and *done = true when every query was answered; *done = false when the caller has to run the general
+// path (not eligible, or a query overflowed its candidate list / has more ties than the fused select sorts).
+static int search_small(isx_store* s, const uint8_t* queries, bool q_on_device, const uint8_t* qlens, size_t Q, uint32_t k,
+                        uint32_t tau_init, const SearchOut& out, bool* done) {
+    *done = false;
+    static const bool env_on = [] { const char* e = getenv("ISX_SMALL_PATH"); return !(e && e[0] == '0'); }();
+    static const uint32_t env_sample = [] { const char* e = getenv("ISX_SMALL_SAMPLE"); return e ? (uint32_t)std::max(1, atoi(e)) : 1u; }();
+    const RankTables& tb = s->tables;
+    const uint32_t R = tb.R;
+    static const size_t env_maxq = [] { const char* e = getenv("ISX_SMALL_MAXQ"); return e ? (size_t)std::max(1, std::min(atoi(e), kSmallT)) : (size_t)4; }();
+    if (!env_on || !s->small_ok || Q > env_maxq || k > kSmallSortCap / 2 || R > kSmallMaxR || s->h_blocks.empty()) return 0;
+    static const bool env_wide = [] { const char* e = getenv("ISX_SMALL_WIDE"); return e ? e[0] != '0' : true; }();
+    static const bool env_hint = [] { const char* e = getenv("ISX_SMALL_L2HINT"); return e ? e[0] != '0' : true; }();
+    const uint32_t chunks = env_wide ? 16 : 8;
+    isx_stats_t& st = s->stats;
+    SmallParams p{};
+    p.l2_evict_first = env_hint ? 1 : 0;
+    // static round-robin units by default; ISX_SMALL_DYNAMIC=1 claims them from a global counter (no tail wait, but
+    // measured 4-8 % slower on 192/256-bit compares, 2 % faster on 64/128-bit: profiles/r02_small_path.txt)
+    static const bool env_dynamic = [] { const char* e = getenv("ISX_SMALL_DYNAMIC"); return e && e[0] == '1'; }();
+    p.static_units = env_dynamic ? 0 : 1;
+    uint32_t max_lq = 0;
+    for (size_t i = 0; i < Q; i++) max_lq = std::max<uint32_t>(max_lq, qlens[i]);
+    uint64_t algo_bytes = 0, pairs = 0, algo_popc = 0;
+    for (uint32_t L = 1; L <= kMaxBytes; L++) {
+        const uint32_t nb = s->bucket_block_lo[L + 1] - s->bucket_block_lo[L];
+        if (!nb) continue;
+        if (p.n_ranges == (uint32_t)kSmallRanges) return 0;
+        SmallRange& rg = p.ranges[p.n_ranges++];
+        rg.we = (std::min(max_lq, L) + 3) / 4;
+        rg.bpu = chunks / rg.we;
+        rg.block0 = s->bucket_block_lo[L];
+        rg.n_blocks = nb;
+        rg.unit0 = p.n_units;
+        rg.n_units = (nb + rg.bpu - 1) / rg.bpu;
+        rg.len_bytes = L;
+        p.n_units += rg.n_units;
+        algo_bytes += s->bucket_rows[L] * std::min(max_lq, L);
+        for (size_t i = 0; i < Q; i++) {
+            const uint32_t m = std::min<uint32_t>(qlens[i], L);
+            pairs += s->bucket_rows[L];
+            algo_popc += s->bucket_rows[L] * ((m + 3) / 4);
+        }
+    }
+    // candidate buffer as in the general path
+    const uint32_t r0 = std::max<uint32_t>(1, (2 * k + kBlockRows - 1) / kBlockRows);
+    uint64_t C64 = std::max<uint64_t>((uint64_t)r0 * kBlockRows + 40ull * k + 2048, 32768);
+    const uint32_t C = (uint32_t)((C64 + 1023) / 1024 * 1024);
+    const size_t state_words = 3 * (size_t)kSmallT + 2 * (size_t)kSmallT * R + 4;   // + the unit counter
+    if (s->d_cand.ensure((size_t)kSmallT * C * 8) || s->h_small_info.ensure(kSmallT * 16) || s->d_out_klo.ensure(Q * (size_t)k * 8)) return ISX_ENOMEM;
+    if (s->small_R != R || s->d_small.cap < state_words * 4) {
+        if (s->d_small.ensure(state_words * 4)) return ISX_ENOMEM;
+        CU(cudaMemsetAsync(s->d_small.p, 0, state_words * 4, s->stream));
+        CU(cudaMemsetAsync(s->d_small.p, 0xff, kSmallT * 4, s->stream));   // tau = ~0
+        s->small_R = R;
+    }
+    uint32_t* base = s->d_small.as<uint32_t>();
+    p.tau = base; p.cand_cnt = base + kSmallT; p.overflow = base + 2 * kSmallT;
+    p.hist = base + 3 * kSmallT; p.shist = p.hist + (size_t)kSmallT * R;
+    p.unit_counter = p.shist + (size_t)kSmallT * R;
+    p.cand = s->d_cand.as<uint64_t>();
+    p.bdesc = s->d_bdesc.as<BlockDesc>();
+    p.segs = s->d_segs.as<SegDesc>();
+    p.T = (uint32_t)Q;
+    p.C = C; p.R = R; p.k = k; p.tau_init = tau_init;
+    p.rank_tab = tb.d_rank.as<uint16_t>();
+    p.hmax_tab = tb.d_hmax.as<uint16_t>();
+    for (size_t i = 0; i < Q; i++) {
+        p.qlen[i] = qlens[i];
+        p.qsrc[i] = (uint32_t)i;
+        if (!q_on_device) memcpy(p.qwords[i], queries + i * 32, 32);
+    }
+    p.d_queries = q_on_device ? reinterpret_cast<const uint32_t*>(queries) : nullptr;
+    const uint32_t grid = (uint32_t)s->sm_count;
+    p.sample_units = env_sample;
+    p.sample_stride = std::max<uint32_t>(1, p.n_units / (grid * p.sample_units));
+    p.out_khi = out.khi; p.out_klo = out.klo ? out.klo : s->d_out_klo.as<uint64_t>(); p.out_h = out.h; p.out_n = out.n;
+    p.out_cnt = out.cnt; p.out_codes = out.codes;
+    if (s->small_host_valid) {
+        p.out_khi = s->small_host_khi; p.out_h = s->small_host_h; p.out_n = s->small_host_n; p.out_cnt = s->small_host_cnt;
+        if (s->key_bytes == 16) p.out_klo = s->small_host_klo;
+    }
+    p.key_words = s->key_bytes == 16 ? 2 : 1;
+    p.info = s->h_small_info.as<uint32_t>();
+    static const bool env_dbg = [] { const char* e = getenv("ISX_SMALL_DEBUG"); return e && e[0] == '1'; }();
+    if (env_dbg) {
+        if (s->h_small_dbg.ensure((size_t)s->sm_count * 128)) return ISX_ENOMEM;
+        memset(s->h_small_dbg.p, 0, (size_t)s->sm_count * 128);
+        p.dbg = s->h_small_dbg.as<unsigned long long>();
+    }
+    const void* kern = env_wide ? (const void*)k_scan_small<3, 16> : (const void*)k_scan_small<5, 8>;
+    const size_t smem = (env_wide ? sizeof(SmallSharedT<3, 16>) : sizeof(SmallSharedT<5, 8>)) + (size_t)Q * R * 4;
+    static int smem_max = -1;
+    if (smem_max < 0) {
+        cudaFuncAttributes fa;
+        CU(cudaFuncGetAttributes(&fa, kern));
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem_optin - (int)fa.sharedSizeBytes));
+        smem_max = s->max_smem_optin - (int)fa.sharedSizeBytes;
+    }
+    if (smem > (size_t)smem_max) return 0;
+    if (s->profiling) CU(cudaEventRecord(s->ev[0], s->stream));
+    void* args[] = {&p};
+    cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kSmallThreads), args, smem, s->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        s->small_ok = false;   // e.g. cooperative launches unsupported under this context (MPS): general path from now on
+        return 0;
+    }
+    if (s->profiling) CU(cudaEventRecord(s->ev[3], s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    st.kernel_launches = 1;
+    st.scan_launches = 1;
+    st.passes = 1;
+    st.pairs = pairs; st.algo_bytes = algo_bytes; st.algo_popc = algo_popc; st.issued_popc = algo_popc;
+    if (s->profiling) {
+        float t = 0;
+        CU(cudaEventElapsedTime(&t, s->ev[0], s->ev[3]));
+        st.total_ms = t;
+        st.scan_ms = t;
+    }
+    if (env_dbg) {
+        const unsigned long long* d = s->h_small_dbg.as<unsigned long long>();
+        for (int b : {0, s->sm_count - 1})
+            fprintf(stderr, "[isx small dbg] cta %3d: setup %llu | phase0 %llu | sync+tau %llu | phase1 %llu | sync %llu | select %llu clk"
+                    " (dstar+list %llu, filter %llu, keys %llu, sort %llu [radix %lld, compact %lld], write %llu) info: cands %u d* %u total_le %u\n", b,
+                    d[b * 16 + 1] - d[b * 16], d[b * 16 + 2] - d[b * 16 + 1], d[b * 16 + 3] - d[b * 16 + 2], d[b * 16 + 4] - d[b * 16 + 3],
+                    d[b * 16 + 5] - d[b * 16 + 4], d[b * 16 + 6] - d[b * 16 + 5], d[b * 16 + 7] - d[b * 16 + 5], d[b * 16 + 8] - d[b * 16 + 7],
+                    d[b * 16 + 9] - d[b * 16 + 8], d[b * 16 + 10] - d[b * 16 + 9], (long long)(d[b * 16 + 12] - d[b * 16 + 9]), (long long)(d[b * 16 + 13] - d[b * 16 + 12]),
+                    d[b * 16 + 11] - d[b * 16 + 10], s->h_small_info.as<uint32_t>()[1], s->h_small_info.as<uint32_t>()[2], s->h_small_info.as<uint32_t>()[3]);
+    }
+    const uint32_t* info = s->h_small_info.as<uint32_t>();
+    bool clean = true;
+    for (size_t i = 0; i < Q; i++) {
+        st.candidates += info[4 * i + 1];
+        if (info[4 * i] != 0) clean = false;
+    }
+    if (!clean) {
+        // rare: candidate overflow (mass duplicates) or more ties than the fused select sorts - the general path
+        // answers the whole batch; the per-query state of the small path is reset
+        CU(cudaMemsetAsync(s->d_small.p, 0, state_words * 4, s->stream));
+        CU(cudaMemsetAsync(s->d_small.p, 0xff, kSmallT * 4, s->stream));
+        return 0;
+    }
+    *done = true;
+    s->small_host_used = s->small_host_valid;
+    return 0;
+}
+
 // Core: all pointers in `out` are DEVICE pointers laid out [Q][k]. `queries` host or device.
 static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, const uint8_t* qlens, size_t Q, uint32_t k,
                        uint32_t thr_num, uint32_t thr_den, const SearchOut& out) {
@@ -500,6 +666,13 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
         uint32_t r = 0;
         while (r + 1 < R && (uint64_t)tb.frac_h[r + 1] * thr_den <= (uint64_t)thr_num * tb.frac_n[r + 1]) r++;
         tau_init = r;
+    }
+
+    {   // one or a handful of queries: the whole search is one cooperative launch (small.cuh)
+        bool done = false;
+        if ((rc = search_small(s, queries, q_on_device, qlens, Q, k, tau_init, out, &done))) return rc;
+        if (done) return 0;
+        st = isx_stats_t{};
     }
 
     // candidate buffer per query: a few k for the logarithmic tail of the running threshold plus slack for the
@@ -801,6 +974,7 @@ int isx_open(isx_store_t** out, int device, uint32_t key_bytes, uint32_t max_byt
     if (prop.major < 10) { delete s; return fail(ISX_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor); }
     s->sm_count = prop.multiProcessorCount;
     s->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    s->small_ok = prop.cooperativeLaunch != 0;
     if (cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete s; return fail(ISX_ECUDA, "cudaStreamCreate failed"); }
     s->stream = s->own_stream;
     for (auto& ev : s->ev)
@@ -835,9 +1009,9 @@ int isx_close(isx_store_t* s) {
     DevBuf* bufs[] = {&s->d_segs, &s->d_blocks, &s->tables.d_rank, &s->tables.d_hmax, &s->d_stage_codes, &s->d_stage_keys,
                       &s->d_stage_dest, &s->d_moves, &s->d_queries, &s->d_tau, &s->d_hist, &s->d_shist, &s->d_cnt, &s->d_ovf, &s->d_cand,
                       &s->d_qmap, &s->d_fb, &s->d_fb_cand, &s->d_out_khi, &s->d_out_klo, &s->d_out_h, &s->d_out_n,
-                      &s->d_out_cnt, &s->d_out_codes, &s->d_bigsort};
+                      &s->d_out_cnt, &s->d_out_codes, &s->d_bigsort, &s->d_bdesc, &s->d_bulk, &s->d_small};
     for (DevBuf* b : bufs) b->release();
-    PinnedBuf* pbufs[] = {&s->h_queries, &s->h_qmap, &s->h_flags, &s->h_out};
+    PinnedBuf* pbufs[] = {&s->h_queries, &s->h_qmap, &s->h_flags, &s->h_out, &s->h_small_info, &s->h_small_dbg};
     for (PinnedBuf* b : pbufs) b->release();
     for (uint32_t r = 0; r < s->share_world; r++)
         if (r != s->share_rank && s->share_ptrs[r]) cudaIpcCloseMemHandle(s->share_ptrs[r]);
@@ -1218,7 +1392,23 @@ int isx_search(isx_store_t* s, const uint8_t* queries, const uint8_t* qlens, siz
         return ISX_ENOMEM;
     SearchOut out{s->d_out_khi.as<uint64_t>(), s->d_out_klo.as<uint64_t>(), s->d_out_h.as<uint16_t>(), s->d_out_n.as<uint16_t>(),
                   s->d_out_cnt.as<uint32_t>(), codes_out ? s->d_out_codes.as<uint8_t>() : nullptr};
-    if ((rc = search_core(s, queries, false, qlens, q, k, thr_num, thr_den, out))) return rc;
+    // pinned result block; the small-batch path lets the device write into it directly
+    const size_t out_bytes = qk * (8 + 8 + 2 + 2) + q * 4;
+    if (s->h_out.ensure(out_bytes)) return ISX_ENOMEM;
+    {
+        uint8_t* hb = s->h_out.as<uint8_t>();
+        s->small_host_khi = reinterpret_cast<uint64_t*>(hb);
+        s->small_host_klo = s->small_host_khi + qk;
+        s->small_host_h = reinterpret_cast<uint16_t*>(s->small_host_klo + qk);
+        s->small_host_n = s->small_host_h + qk;
+        s->small_host_cnt = reinterpret_cast<uint32_t*>(s->small_host_n + qk);
+        s->small_host_valid = !first_of_asset_out;   // the grouping kernel reads the device copy
+        s->small_host_used = false;
+    }
+    rc = search_core(s, queries, false, qlens, q, k, thr_num, thr_den, out);
+    s->small_host_valid = false;
+    if (rc) return rc;
+    const bool direct = s->small_host_used;
     if (first_of_asset_out) {
         // device-side grouping of simprint matches: flag the best record of every asset per query
         uint32_t H = 2;
@@ -1233,19 +1423,19 @@ int isx_search(isx_store_t* s, const uint8_t* queries, const uint8_t* qlens, siz
         CU(cudaMemcpyAsync(first_of_asset_out, s->d_stage_codes.p, qk, cudaMemcpyDeviceToHost, s->stream));
     }
     // results -> pinned staging -> caller
-    size_t bytes = qk * (8 + 8 + 2 + 2) + q * 4;
-    if (s->h_out.ensure(bytes)) return ISX_ENOMEM;
     uint8_t* h = s->h_out.as<uint8_t>();
     uint64_t* h_khi = reinterpret_cast<uint64_t*>(h);
     uint64_t* h_klo = h_khi + qk;
     uint16_t* h_h = reinterpret_cast<uint16_t*>(h_klo + qk);
     uint16_t* h_n = h_h + qk;
     uint32_t* h_cnt = reinterpret_cast<uint32_t*>(h_n + qk);
-    CU(cudaMemcpyAsync(h_khi, out.khi, qk * 8, cudaMemcpyDeviceToHost, s->stream));
-    if (s->key_bytes == 16) CU(cudaMemcpyAsync(h_klo, out.klo, qk * 8, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(h_h, out.h, qk * 2, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(h_n, out.n, qk * 2, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(h_cnt, out.cnt, q * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (!direct) {
+        CU(cudaMemcpyAsync(h_khi, out.khi, qk * 8, cudaMemcpyDeviceToHost, s->stream));
+        if (s->key_bytes == 16) CU(cudaMemcpyAsync(h_klo, out.klo, qk * 8, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(h_h, out.h, qk * 2, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(h_n, out.n, qk * 2, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(h_cnt, out.cnt, q * 4, cudaMemcpyDeviceToHost, s->stream));
+    }
     if (codes_out) CU(cudaMemcpyAsync(codes_out, out.codes, qk * 32, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     memcpy(hamming_out, h_h, qk * 2);

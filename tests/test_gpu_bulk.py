@@ -107,7 +107,7 @@ def test_bulk_append_uniform_length_128bit_keys_threshold_and_join(cuda):
     l8 = np.full(n, 8, dtype=np.uint8)
     codes = synth.make_codes(0, n, seed, l8, dup_every=16, dup_back=65)
     hi, lo = synth.make_keys128(0, n, seed, 64)
-    qs = np.ascontiguousarray(codes[[14, 206, 4110, 77_777, 150_001]])
+    qs = np.ascontiguousarray(codes[[14, 206, 4110, 77_774, 150_014]])
     ql = np.full(5, 8, dtype=np.uint8)
     for kk, thr in ((300, (16, 64)), (1000, (0, 64))):
         gk, gh, gn, gc, _ = st.search(qs, ql, kk, thr)
