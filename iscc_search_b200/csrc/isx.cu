@@ -1414,9 +1414,13 @@ int isx_search(isx_store_t* s, const uint8_t* queries, const uint8_t* qlens, siz
         uint32_t H = 2;
         while (H < 2 * k) H <<= 1;
         const size_t smem = (size_t)H * 12 + 16;
-        if (smem + 1024 > (size_t)s->max_smem_optin) return fail(ISX_ELIMIT, "first_of_asset_out supports count <= %u", (uint32_t)(s->max_smem_optin / 24 / 2));
+        if (smem + 2048 > (size_t)s->max_smem_optin) return fail(ISX_ELIMIT, "first_of_asset_out supports count <= %u", (uint32_t)(s->max_smem_optin / 24 / 2));
         if (s->d_stage_codes.ensure(qk)) return ISX_ENOMEM;
-        CU(cudaFuncSetAttribute(k_first_per_asset, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem_optin - 64));
+        {
+            cudaFuncAttributes fa;
+            CU(cudaFuncGetAttributes(&fa, k_first_per_asset));
+            CU(cudaFuncSetAttribute(k_first_per_asset, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem_optin - (int)fa.sharedSizeBytes));
+        }
         k_first_per_asset<<<(unsigned)q, 512, smem, s->stream>>>(out.khi, out.cnt, k, H, s->d_stage_codes.as<uint8_t>());
         CU(cudaGetLastError());
         s->stats.kernel_launches++;
