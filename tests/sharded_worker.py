@@ -39,7 +39,7 @@ if args.backend == "nccl":
     inv = np.argsort(perm)
     # third batch: 150K extra rows sharing ONE code -> every rank's candidate buffer overflows for that query and the
     # exact re-scan path runs while thresholds are shared; the merged result must be the 100 smallest keys among the ties
-    dup_n = 150_000
+    dup_n = 45_000 * world   # > the candidate buffer (32768) on every rank
     dup_keys = synth.make_keys(10**9, dup_n, 77)
     dup_codes = np.zeros((dup_n, 32), dtype=np.uint8)
     dup_codes[:, :16] = 0xA7
