@@ -46,6 +46,7 @@ static int fail(int code, const char* fmt, ...) {
 constexpr uint32_t kMinSegRows = 4096;
 constexpr uint32_t kMaxSegRows = 1u << kRowBits;  // 4 Mi rows
 constexpr uint32_t kBlockRows = kRowsPerStep;     // 1024
+constexpr int kMaxLanes = 4;                      // query tiles of one batch in flight at a time (each with its own per-query state)
 constexpr uint32_t kMaxK = 65536;                 // beyond the shared-memory sort capacity winners are sorted in global scratch
 
 // growable device buffer
@@ -122,6 +123,11 @@ struct isx_store {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};  // the launches of one pass run concurrently (tails overlap)
     cudaEvent_t fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
+    // two tile lanes: consecutive query tiles of a batch run on alternating streams with their own per-query state, so the
+    // bootstrap / select of one tile and the tail of its scan launches overlap the next tile's scan
+    cudaStream_t lane_stream[kMaxLanes] = {}, lane_side[kMaxLanes][3] = {};
+    cudaEvent_t lane_fork[kMaxLanes] = {}, lane_join[kMaxLanes][3] = {};
+    cudaEvent_t lanes_begin = nullptr, lane_done[kMaxLanes] = {};
     bool profiling = false;
 
     std::shared_mutex rows_mu;  // shared: search/get/contains; exclusive: add/remove/clear/load
@@ -410,7 +416,11 @@ static int launch_scan(isx_store* s, ScanParams& p, uint32_t we, uint32_t bpi_hi
 
 // Scan block range [b0, b1) of the global block list for one tile of queries; the range may span
 // several buckets, each bucket portion is one launch (uniform compared length).
-static int scan_range(isx_store* s, ScanParams& p, uint32_t b0, uint32_t b1, uint32_t bpi_hint) {
+static int scan_range(isx_store* s, ScanParams& p, uint32_t b0, uint32_t b1, uint32_t bpi_hint, int lane = -1) {
+    cudaStream_t main_stream = lane < 0 ? s->stream : s->lane_stream[lane];
+    cudaStream_t* sides = lane < 0 ? s->side : s->lane_side[lane];
+    cudaEvent_t fork_ev = lane < 0 ? s->fork_ev : s->lane_fork[lane];
+    cudaEvent_t* join_ev = lane < 0 ? s->join_ev : s->lane_join[lane];
     // buckets with L >= Lq all compare m = Lq bytes: they form ONE launch; shorter buckets one launch each.
     // The launches of a pass are independent (they only share the monotone thresholds), so the 2nd..4th go to
     // side streams forked from / joined back into the store's stream: their ramp-up and tails overlap.
@@ -422,16 +432,16 @@ static int scan_range(isx_store* s, ScanParams& p, uint32_t b0, uint32_t b1, uin
             uint32_t m = std::min(p.qlen_bytes, L);
             p.block_begin = lo;
             p.block_end = hi;
-            cudaStream_t stream = s->stream;
+            cudaStream_t stream = main_stream;
             if (n_launch > 0 && side_used < 3) {
-                if (side_used == 0) CU(cudaEventRecord(s->fork_ev, s->stream));
-                stream = s->side[side_used];
-                CU(cudaStreamWaitEvent(stream, s->fork_ev, 0));
+                if (side_used == 0) CU(cudaEventRecord(fork_ev, main_stream));
+                stream = sides[side_used];
+                CU(cudaStreamWaitEvent(stream, fork_ev, 0));
             }
             int rc = launch_scan(s, p, (m + 3) / 4, bpi_hint, stream);
             if (rc) return rc;
-            if (stream != s->stream) {
-                CU(cudaEventRecord(s->join_ev[side_used], stream));
+            if (stream != main_stream) {
+                CU(cudaEventRecord(join_ev[side_used], stream));
                 side_used++;
             }
             n_launch++;
@@ -453,7 +463,7 @@ static int scan_range(isx_store* s, ScanParams& p, uint32_t b0, uint32_t b1, uin
         }
         if (Lhi == kMaxBytes) break;
     }
-    for (int i = 0; i < side_used; i++) CU(cudaStreamWaitEvent(s->stream, s->join_ev[i], 0));
+    for (int i = 0; i < side_used; i++) CU(cudaStreamWaitEvent(main_stream, join_ev[i], 0));
     return 0;
 }
 
@@ -693,12 +703,16 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
     if (k > cap_max) {  // large k: global-memory sort scratch, one region per query of the tile
         big_P = 1;
         while (big_P < k) big_P <<= 1;
-        if (s->d_bigsort.ensure((size_t)tile_max * big_P * sizeof(BigRec))) return ISX_ENOMEM;
+        if (s->d_bigsort.ensure((size_t)kMaxLanes * tile_max * big_P * sizeof(BigRec))) return ISX_ENOMEM;
     }
-    if (s->d_queries.ensure(Q * 32) || s->d_qmap.ensure(Q * 4) || s->d_tau.ensure((size_t)tile_max * 4) ||
-        s->d_hist.ensure((size_t)tile_max * R * 4) || s->d_shist.ensure((size_t)tile_max * R * 4) || s->d_cnt.ensure((size_t)tile_max * 4) ||
-        s->d_ovf.ensure((size_t)tile_max * 4) || s->d_cand.ensure((size_t)tile_max * C * 8) ||
-        s->d_fb.ensure((size_t)tile_max * 8) || s->h_flags.ensure((size_t)tile_max * 16))
+    // per-query state of a tile, twice (two tile lanes) when the batch has more than one tile
+    static const size_t env_lanes = [] { const char* e = getenv("ISX_TILE_LANES"); return e ? (size_t)std::max(1, std::min(atoi(e), kMaxLanes)) : (size_t)2; }();
+    const bool multi_tile = Q > tile_max || [&] { uint32_t m = 0; for (size_t i = 0; i < Q; i++) m |= 1u << (qlens[i] - 1); return (m & (m - 1)) != 0; }();
+    const size_t n_sets = multi_tile ? env_lanes : 1;
+    if (s->d_queries.ensure(Q * 32) || s->d_qmap.ensure(Q * 4) || s->d_tau.ensure(n_sets * tile_max * 4) ||
+        s->d_hist.ensure(n_sets * tile_max * R * 4) || s->d_shist.ensure(n_sets * tile_max * R * 4) || s->d_cnt.ensure(n_sets * tile_max * 4) ||
+        s->d_ovf.ensure(n_sets * tile_max * 4) || s->d_cand.ensure(n_sets * tile_max * C * 8) ||
+        s->d_fb.ensure(n_sets * tile_max * 8) || s->h_flags.ensure((size_t)tile_max * 16))
         return ISX_ECUDA;
 
     // queries in group order on the device + the map back to original positions
@@ -760,18 +774,18 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
 
     // shared (cross-rank) histograms need every rank to see the same query batch in the same order
     const bool share_on = s->share_world > 1 && share_armed && R <= isx_store::kShareRcap && Q <= s->share_maxq;
-    auto make_params = [&](const Tile& t) {
+    auto make_params = [&](const Tile& t, size_t set = 0) {
         ScanParams p{};
         p.segs = s->d_segs.as<SegDesc>();
         p.blocks = s->d_blocks.as<uint2>();
         p.queries = s->d_queries.as<uint32_t>() + t.t0 * 8;
         p.T = t.T;
         p.qlen_bytes = t.Lq;
-        p.tau = s->d_tau.as<uint32_t>();
-        p.hist = s->d_hist.as<uint32_t>();
-        p.cand_cnt = s->d_cnt.as<uint32_t>();
-        p.cand = s->d_cand.as<uint64_t>();
-        p.overflow = s->d_ovf.as<uint32_t>();
+        p.tau = s->d_tau.as<uint32_t>() + set * tile_max;
+        p.hist = s->d_hist.as<uint32_t>() + set * tile_max * R;
+        p.cand_cnt = s->d_cnt.as<uint32_t>() + set * tile_max;
+        p.cand = s->d_cand.as<uint64_t>() + set * tile_max * C;
+        p.overflow = s->d_ovf.as<uint32_t>() + set * tile_max;
         p.C = C; p.R = R; p.k = k;
         p.rank_tab = tb.d_rank.as<uint16_t>();
         p.hmax_tab = tb.d_hmax.as<uint16_t>();
@@ -784,7 +798,7 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
         }
         return p;
     };
-    auto make_select = [&](const Tile& t, const ScanParams& p) {
+    auto make_select = [&](const Tile& t, const ScanParams& p, size_t set = 0) {
         SelectParams sp{};
         sp.segs = p.segs; sp.hist = p.hist; sp.cand_cnt = p.cand_cnt; sp.cand = p.cand; sp.overflow = p.overflow;
         sp.qmap = s->d_qmap.as<uint32_t>() + t.t0;
@@ -792,27 +806,36 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
         sp.tau_init = tau_init;
         sp.out_khi = out.khi; sp.out_klo = out.klo; sp.out_h = out.h; sp.out_n = out.n; sp.out_cnt = out.cnt;
         sp.out_codes = out.codes;
-        sp.fallback_info = s->d_fb.as<uint32_t>();
+        sp.fallback_info = s->d_fb.as<uint32_t>() + set * tile_max * 2;
         sp.skip_overflowed = 1;
-        sp.big_scratch = big_P ? s->d_bigsort.as<BigRec>() : nullptr;
+        sp.big_scratch = big_P ? s->d_bigsort.as<BigRec>() + set * tile_max * big_P : nullptr;
         sp.big_P = big_P;
         return sp;
     };
 
+    const bool lanes = n_sets > 1 && tiles.size() > 1;
+    if (lanes) {   // the tile lanes start after everything enqueued so far (query upload, tables)
+        CU(cudaEventRecord(s->lanes_begin, s->stream));
+        for (size_t l = 0; l < n_sets; l++) CU(cudaStreamWaitEvent(s->lane_stream[l], s->lanes_begin, 0));
+    }
     for (size_t ti = 0; ti < tiles.size(); ti++) {
         const Tile& t = tiles[ti];
         const uint32_t T = t.T, Lq = t.Lq;
+        const int lane = lanes ? (int)(ti % n_sets) : -1;
+        const size_t set = lanes ? (ti % n_sets) : 0;
+        cudaStream_t ts = lanes ? s->lane_stream[lane] : s->stream;
+        uint32_t* d_shist = s->d_shist.as<uint32_t>() + set * tile_max * R;
         st.passes++;
-        ScanParams p = make_params(t);
+        ScanParams p = make_params(t, set);
         {
             size_t total = (size_t)T * R;
             uint32_t grid = (uint32_t)std::min<size_t>((total + 255) / 256, (size_t)s->sm_count * 8);
             grid = std::max<uint32_t>(grid, (T + 255) / 256);
-            k_init_queries<<<grid, 256, 0, s->stream>>>(p.tau, p.hist, s->d_shist.as<uint32_t>(), p.cand_cnt, p.overflow, T, R, tau_init);
+            k_init_queries<<<grid, 256, 0, ts>>>(p.tau, p.hist, d_shist, p.cand_cnt, p.overflow, T, R, tau_init);
             CU(cudaGetLastError());
             st.kernel_launches++;
         }
-        if (s->profiling) CU(cudaEventRecord(s->tile_events[3 * ti], s->stream));
+        if (s->profiling) CU(cudaEventRecord(s->tile_events[3 * ti], ts));
         // threshold bootstrap from a stratified row sample (no emission), then one launch per compared length
         if (n_blocks_total > 0) {
             // batches: 64 blocks, refined by the two warm-up ranges below; small tiles: ~1 % of the store, because
@@ -830,9 +853,9 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
             }
             sp.prefix[kMaxBytes + 1] = total;
             size_t smem = (size_t)R * 4 + 258 * 2 + 16;
-            k_sample<<<dim3(total, T, 1), kThreads, smem, s->stream>>>(p, sp, s->d_shist.as<uint32_t>());
+            k_sample<<<dim3(total, T, 1), kThreads, smem, ts>>>(p, sp, d_shist);
             CU(cudaGetLastError());
-            k_sample_tau<<<(T * 32 + 255) / 256, 256, 0, s->stream>>>(s->d_shist.as<uint32_t>(), p.tau, T, R, k);
+            k_sample_tau<<<(T * 32 + 255) / 256, 256, 0, ts>>>(d_shist, p.tau, T, R, k);
             CU(cudaGetLastError());
             st.kernel_launches += 2;
         }
@@ -844,23 +867,29 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
         if (T >= 64) {
             for (uint32_t span : {64u, 512u}) {
                 if (n_blocks_total - done <= span * 4) break;
-                if ((rc = scan_range(s, p, done, done + span, bpi_main))) return rc;
+                if ((rc = scan_range(s, p, done, done + span, bpi_main, lane))) return rc;
                 done += span;
             }
         }
-        if ((rc = scan_range(s, p, done, n_blocks_total, bpi_main))) return rc;
-        if (s->profiling) CU(cudaEventRecord(s->tile_events[3 * ti + 1], s->stream));
+        if ((rc = scan_range(s, p, done, n_blocks_total, bpi_main, lane))) return rc;
+        if (s->profiling) CU(cudaEventRecord(s->tile_events[3 * ti + 1], ts));
 
-        SelectParams sp = make_select(t, p);
-        k_select<<<T, kSelectThreads, sel_smem, s->stream>>>(sp);
+        SelectParams sp = make_select(t, p, set);
+        k_select<<<T, kSelectThreads, sel_smem, ts>>>(sp);
         CU(cudaGetLastError());
         st.kernel_launches++;
-        if (s->profiling) CU(cudaEventRecord(s->tile_events[3 * ti + 2], s->stream));
-        // per-tile flags to pinned memory, no synchronisation (the state buffers are reused by the next tile in stream order)
-        CU(cudaMemcpyAsync(hf_ovf + t.t0, p.overflow, (size_t)T * 4, cudaMemcpyDeviceToHost, s->stream));
-        CU(cudaMemcpyAsync(hf_cnt + t.t0, p.cand_cnt, (size_t)T * 4, cudaMemcpyDeviceToHost, s->stream));
-        CU(cudaMemcpyAsync(hf_info + 2 * t.t0, sp.fallback_info, (size_t)T * 8, cudaMemcpyDeviceToHost, s->stream));
+        if (s->profiling) CU(cudaEventRecord(s->tile_events[3 * ti + 2], ts));
+        // per-tile flags to pinned memory, no synchronisation (the state buffers are reused two tiles later in stream order)
+        CU(cudaMemcpyAsync(hf_ovf + t.t0, p.overflow, (size_t)T * 4, cudaMemcpyDeviceToHost, ts));
+        CU(cudaMemcpyAsync(hf_cnt + t.t0, p.cand_cnt, (size_t)T * 4, cudaMemcpyDeviceToHost, ts));
+        CU(cudaMemcpyAsync(hf_info + 2 * t.t0, sp.fallback_info, (size_t)T * 8, cudaMemcpyDeviceToHost, ts));
         (void)Lq;
+    }
+    if (lanes) {
+        for (size_t l = 0; l < n_sets; l++) {
+            CU(cudaEventRecord(s->lane_done[l], s->lane_stream[l]));
+            CU(cudaStreamWaitEvent(s->stream, s->lane_done[l], 0));
+        }
     }
     CU(cudaStreamSynchronize(s->stream));
     if (s->profiling) {
@@ -984,6 +1013,18 @@ int isx_open(isx_store_t** out, int device, uint32_t key_bytes, uint32_t max_byt
             cudaEventCreateWithFlags(&s->join_ev[i], cudaEventDisableTiming) != cudaSuccess) { delete s; return fail(ISX_ECUDA, "side stream setup failed"); }
     }
     if (cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming) != cudaSuccess) { delete s; return fail(ISX_ECUDA, "cudaEventCreate failed"); }
+    {
+        bool ok = cudaEventCreateWithFlags(&s->lanes_begin, cudaEventDisableTiming) == cudaSuccess;
+        for (int l = 0; l < kMaxLanes && ok; l++) {
+            ok = ok && cudaStreamCreateWithFlags(&s->lane_stream[l], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&s->lane_fork[l], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&s->lane_done[l], cudaEventDisableTiming) == cudaSuccess;
+            for (int i = 0; i < 3 && ok; i++)
+                ok = cudaStreamCreateWithFlags(&s->lane_side[l][i], cudaStreamNonBlocking) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&s->lane_join[l][i], cudaEventDisableTiming) == cudaSuccess;
+        }
+        if (!ok) { delete s; return fail(ISX_ECUDA, "tile lane stream setup failed"); }
+    }
     *out = s;
     return 0;
 }
@@ -1020,6 +1061,13 @@ int isx_close(isx_store_t* s) {
     for (auto& ev : s->tile_events) cudaEventDestroy(ev);
     for (int i = 0; i < 3; i++) { if (s->side[i]) cudaStreamDestroy(s->side[i]); if (s->join_ev[i]) cudaEventDestroy(s->join_ev[i]); }
     if (s->fork_ev) cudaEventDestroy(s->fork_ev);
+    if (s->lanes_begin) cudaEventDestroy(s->lanes_begin);
+    for (int l = 0; l < kMaxLanes; l++) {
+        for (int i = 0; i < 3; i++) { if (s->lane_side[l][i]) cudaStreamDestroy(s->lane_side[l][i]); if (s->lane_join[l][i]) cudaEventDestroy(s->lane_join[l][i]); }
+        if (s->lane_fork[l]) cudaEventDestroy(s->lane_fork[l]);
+        if (s->lane_done[l]) cudaEventDestroy(s->lane_done[l]);
+        if (s->lane_stream[l]) cudaStreamDestroy(s->lane_stream[l]);
+    }
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
     return 0;
