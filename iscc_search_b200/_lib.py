@@ -13,7 +13,7 @@ from pathlib import Path
 import numpy as np
 
 _PKG = Path(__file__).resolve().parent
-SO_PATH = _PKG / "libisx_b200.so"
+SO_PATH = Path(os.environ["ISX_LIB_PATH"]).resolve() if os.environ.get("ISX_LIB_PATH") else _PKG / "libisx_b200.so"  # override: A/B of builds
 CSRC = _PKG / "csrc"
 
 ISX_EINVAL, ISX_ECUDA, ISX_ENOMEM, ISX_EIO, ISX_ELIMIT = -1, -2, -3, -4, -5

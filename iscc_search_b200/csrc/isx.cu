@@ -365,7 +365,7 @@ static int build_tables(isx_store* s, uint32_t mask) {
 template <int WE, int G, int MINB = 3>
 static int launch_scan_t(isx_store* s, const ScanParams& p, uint32_t grid_cap_per_sm, cudaStream_t stream) {
     constexpr int QW = (WE <= 4) ? 4 : 8;
-    size_t smem = (size_t)p.q_split * (QW * 4 + 4 + 1) + 258 * 2 + ((size_t)p.R + 2) * 2 + 16;
+    size_t smem = (size_t)p.q_split * (QW * 4 + 2) + 4 + 258 * 2 + ((size_t)p.R + 2) * 2 + 32;
     static bool attr_done = false;
     if (!attr_done || smem > 48 * 1024) {
         CU(cudaFuncSetAttribute(k_scan<WE, G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem_optin));
@@ -790,6 +790,12 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
         p.rank_tab = tb.d_rank.as<uint16_t>();
         p.hmax_tab = tb.d_hmax.as<uint16_t>();
         p.update_tau = 1;
+        {   // threshold feedback every ~k/4 new candidates of a query (power of two, >= 16)
+            uint32_t step = std::max<uint32_t>(k / 4, 16), sh = 0;
+            while ((2u << sh) <= step) sh++;
+            static const int env_shift = [] { const char* e = getenv("ISX_TIGHTEN_SHIFT"); return e ? atoi(e) : -1; }();
+            p.tighten_shift = env_shift >= 0 ? (uint32_t)env_shift : sh;
+        }
         if (share_on) {
             for (uint32_t r = 0; r < s->share_world; r++) p.g_hist[r] = s->share_ptrs[r];
             p.g_world = s->share_world;

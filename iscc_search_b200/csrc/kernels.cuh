@@ -59,6 +59,7 @@ struct ScanParams {
     const uint16_t* rank_tab;    // [33][257]: rank of h/(8m)
     const uint16_t* hmax_tab;    // [33][R]:  max h with rank(m, h) <= r
     uint32_t update_tau;         // 0: fixed threshold (exact re-scan)
+    uint32_t tighten_shift;      // a query's threshold is re-derived whenever its candidate count crosses a multiple of 2^shift
     uint32_t q_split;            // queries per CTA along gridDim.y (small ranges are split over queries
                                  // so the bootstrap rounds still fill the chip)
     // Cross-rank threshold sharing (multi-GPU): rank histograms of ALL ranks are summed in peer memory
@@ -86,15 +87,61 @@ __device__ __forceinline__ uint4 ldg_stream(const uint32_t* p) {
     return r;
 }
 
+__device__ __forceinline__ uint32_t ld_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p));  // peer memory: never a stale L1 line
+    return v;
+}
+
+// Tighten tau[q] to the smallest rank t with (observed) sum_{r<=t} hist[q][r] >= k. Observed counts only under-count, so
+// t is always >= the true k-th rank. One warp; the bins are fetched 8 x 32 at a time (one round trip to L2 - or over
+// NVLink to the home rank of the shared histograms - per 256 ranks instead of one per 32).
+__device__ __noinline__ void tighten_tau(const ScanParams& p, uint32_t q, uint32_t lane) {
+    const uint32_t tcur = __ldcg(&p.tau[q]);
+    const bool shared = p.g_world != 0;
+    const uint32_t gq = p.g_q0 + q;
+    const uint32_t* hq = shared ? p.g_hist[gq % p.g_world] + (size_t)(gq / p.g_world) * p.g_rcap : p.hist + (size_t)q * p.R;
+    uint32_t cum = 0;
+    for (uint32_t base = 0; base <= tcur; base += 256) {
+        uint32_t v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t r = base + 32 * j + lane;
+            v[j] = (r <= tcur) ? (shared ? ld_sys(&hq[r]) : __ldcg(&hq[r])) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            uint32_t incl = v[j];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (uint32_t)o) incl += t;
+            }
+            const unsigned hit = __ballot_sync(0xffffffffu, cum + incl >= p.k);
+            if (hit) {
+                const uint32_t t = base + 32 * j + (uint32_t)(__ffs(hit) - 1);
+                if (lane == 0 && t < tcur) atomicMin(&p.tau[q], t);
+                return;
+            }
+            cum += __shfl_sync(0xffffffffu, incl, 31);
+            if (base + 32 * (j + 1) > tcur) return;
+        }
+    }
+}
+
 // Rare path, entered by the WHOLE warp when any lane has a row within the running threshold of
 // query q: per row slot one ballot, one slot-allocating atomic per warp, fire-and-forget histogram
 // updates. `s_rank` is the rank row of this launch's compared length (shared memory).
+// Threshold feedback lives here too: the warp whose emission makes the query's candidate count cross a multiple of
+// 2^tighten_shift (~k/4 new candidates anywhere on this GPU) re-derives the threshold from the histogram. The
+// threshold follows "k rows found" only logarithmically in the rows scanned, so that is ~100 re-derivations per query
+// and search instead of one per CTA and work item in which the query emitted (which cost 25 % of a small shard's scan).
 __device__ __noinline__ void emit_group(const ScanParams& p, uint32_t q, uint32_t hmax, uint32_t d0, uint32_t d1, uint32_t d2,
                                         uint32_t d3, uint32_t seg, uint32_t row0, uint32_t seg_n, const uint16_t* s_rank,
                                         unsigned char* dirty) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t d[4] = {d0, d1, d2, d3};
-    bool any = false;
+    bool any = false, crossed = false;
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         const bool e = (d[r] <= hmax) && (row0 + r < seg_n);  // padding rows of the last block never emit
@@ -105,6 +152,7 @@ __device__ __noinline__ void emit_group(const ScanParams& p, uint32_t q, uint32_
         uint32_t base = 0;
         if ((int)lane == leader) base = atomicAdd(&p.cand_cnt[q], (uint32_t)__popc(bal));
         base = __shfl_sync(0xffffffffu, base, leader);
+        crossed |= ((base + (uint32_t)__popc(bal)) >> p.tighten_shift) != (base >> p.tighten_shift);
         if (e) {
             const uint32_t rank = s_rank[d[r]];
             atomicAdd(&p.hist[(size_t)q * p.R + rank], 1u);
@@ -117,39 +165,10 @@ __device__ __noinline__ void emit_group(const ScanParams& p, uint32_t q, uint32_
             else p.overflow[q] = 1u;
         }
     }
-    if (any && lane == 0) dirty[q] = 1;
-}
-
-// Tighten tau[q] to the smallest rank t with (observed) sum_{r<=t} hist[q][r] >= k. Observed counts
-// only under-count, so t is always >= the true k-th rank. One warp per query.
-__device__ __forceinline__ uint32_t ld_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p));  // peer memory: never a stale L1 line
-    return v;
-}
-
-__device__ __forceinline__ void tighten_tau(const ScanParams& p, uint32_t q, uint32_t lane) {
-    uint32_t tcur = __ldcg(&p.tau[q]);
-    const bool shared = p.g_world != 0;
-    const uint32_t gq = p.g_q0 + q;
-    const uint32_t* hq = shared ? p.g_hist[gq % p.g_world] + (size_t)(gq / p.g_world) * p.g_rcap : p.hist + (size_t)q * p.R;
-    uint32_t cum = 0;
-    for (uint32_t base = 0; base <= tcur; base += 32) {
-        uint32_t r = base + lane;
-        uint32_t v = (r <= tcur) ? (shared ? ld_sys(&hq[r]) : __ldcg(&hq[r])) : 0u;
-        uint32_t incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= (uint32_t)o) incl += t;
-        }
-        unsigned hit = __ballot_sync(0xffffffffu, cum + incl >= p.k);
-        if (hit) {
-            uint32_t t = base + (uint32_t)(__ffs(hit) - 1);
-            if (lane == 0 && t < tcur) atomicMin(&p.tau[q], t);
-            return;
-        }
-        cum += __shfl_sync(0xffffffffu, incl, 31);
+    if (dirty && any && lane == 0) dirty[q] = 1;
+    if (crossed && p.update_tau) {
+        __threadfence();   // this warp's own counts are visible to the sweep (others' are at worst missed: under-count)
+        tighten_tau(p, q, lane);
     }
 }
 
@@ -216,14 +235,13 @@ struct LowerBound {
         uint32_t acc = 0;
         ISX_UNROLL
         for (int w = 0; w < WE; w += F) {
-            uint32_t t = 0;
+            // the fold that holds the last word starts with it: (a ^ q) & mask is ONE LOP3 there, and every further
+            // word of a fold is one LOP3 (t | (a ^ q)); starting from an unmasked word costs an extra instruction
+            const bool has_last = (w + F >= WE);
+            uint32_t t = has_last ? ((comp(a[WE - 1], r) ^ qv[WE - 1]) & mask_last) : 0u;
             ISX_UNROLL
             for (int j = 0; j < F; j++) {
-                if (w + j < WE) {
-                    uint32_t x = comp(a[w + j], r) ^ qv[w + j];
-                    if (w + j == WE - 1) x &= mask_last;
-                    t |= x;
-                }
+                if (w + j < WE && !(has_last && w + j == WE - 1)) t |= comp(a[w + j], r) ^ qv[w + j];
             }
             acc += popc32(t);
         }
@@ -247,16 +265,14 @@ __global__ void __launch_bounds__(kThreads, MINB) k_scan(const __grid_constant__
     const uint32_t q0 = blockIdx.y * p.q_split;                 // first query of this CTA's sub-tile
     const uint32_t T = min(p.q_split, p.T - q0);
     uint32_t* qw = reinterpret_cast<uint32_t*>(smem_raw);       // [q_split][QW]
-    uint32_t* hm = qw + (size_t)p.q_split * QW;                 // [q_split]
-    uint16_t* s_rank = reinterpret_cast<uint16_t*>(hm + p.q_split);  // [258] rank of h at this compared length
+    uint16_t* hm = reinterpret_cast<uint16_t*>(qw + (size_t)p.q_split * QW);   // [q_split] bound | tier << 12 (h <= 256 needs 9 bits)
+    uint16_t* s_rank = hm + ((p.q_split + 1) & ~1u);                 // [258] rank of h at this compared length
     uint16_t* s_hrow = s_rank + 258;                                 // [R rounded up to even] largest h within rank r
-    unsigned char* dirty = reinterpret_cast<unsigned char*>(s_hrow + ((p.R + 1) & ~1u));  // [q_split]
 
     for (uint32_t i = tid; i < T * QW; i += kThreads) {
         uint32_t q = i / QW, w = i % QW;
         qw[i] = (w < WE) ? p.queries[(size_t)(q0 + q) * 8 + w] : 0u;
     }
-    for (uint32_t q = tid; q < T; q += kThreads) dirty[q] = 0;
 
     // every block of this launch belongs to one bucket: m, the last-word mask and the threshold row are uniform
     const uint32_t seg_len = p.segs[p.blocks[p.block_begin].x].len_bytes;
@@ -274,8 +290,13 @@ __global__ void __launch_bounds__(kThreads, MINB) k_scan(const __grid_constant__
     const uint32_t my_hi = min(p.block_end, p.block_begin + G * (uint32_t)(n_groups * (blockIdx.x + 1) / gridDim.x));
     // small tiles (one query per thread at most): the next item's bound is fetched while this item streams
     const bool prefetch = (T <= kThreads);
-    uint32_t hm_next = 0;
-    if (prefetch && tid < T) hm_next = hrow[__ldcg(&p.tau[q0 + tid])];
+    // bound of a query + its filter tier (uniform per query): 3 = folds of three words, 2 = folds of two, 0 = none
+    auto pack_bound = [](uint32_t h) -> uint16_t {
+        const uint32_t tier = h <= LowerBound<WE>::kCutoff3 ? 3u : h <= LowerBound<WE>::kCutoff2 ? 2u : 0u;
+        return (uint16_t)(h | (tier << 12));
+    };
+    uint16_t hm_next = 0;
+    if (prefetch && tid < T) hm_next = pack_bound(hrow[__ldcg(&p.tau[q0 + tid])]);
 
     // item size ramps G, 2G, 4G .. blocks_per_item: the first bounds a CTA works with are the loosest
     uint32_t item_blocks = p.update_tau ? G : p.blocks_per_item;
@@ -286,10 +307,10 @@ __global__ void __launch_bounds__(kThreads, MINB) k_scan(const __grid_constant__
         if (prefetch && n_items_done >= 3) {                  // steady state: bound fetched during the previous item
             if (tid < T) hm[tid] = hm_next;
         } else {                                              // ramp-up items: always the freshest bound
-            for (uint32_t q = tid; q < T; q += kThreads) hm[q] = hrow[__ldcg(&p.tau[q0 + q])];
+            for (uint32_t q = tid; q < T; q += kThreads) hm[q] = pack_bound(hrow[__ldcg(&p.tau[q0 + q])]);
         }
         __syncthreads();
-        if (prefetch && tid < T && p.update_tau) hm_next = hrow[__ldcg(&p.tau[q0 + tid])];  // lands during the item
+        if (prefetch && tid < T && p.update_tau) hm_next = pack_bound(hrow[__ldcg(&p.tau[q0 + tid])]);  // lands during the item
 
         for (uint32_t b = b_lo; b < b_hi; b += G) {
             uint4 a[G][WE];
@@ -326,9 +347,9 @@ __global__ void __launch_bounds__(kThreads, MINB) k_scan(const __grid_constant__
                         if (WE > 7) qv[7] = v1.w;
                     }
                 }
-                const uint32_t hmax = hm[q];
-                // filter tier, uniform per query: 3 = folds of three words, 2 = folds of two, 0 = none
-                const int tier = hmax <= LowerBound<WE>::kCutoff3 ? 3 : hmax <= LowerBound<WE>::kCutoff2 ? 2 : 0;
+                const uint32_t hv = hm[q];
+                const uint32_t hmax = hv & 0xfffu;
+                const uint32_t tier = hv >> 12;   // filter tier, uniform per query
 #pragma unroll
                 for (int g = 0; g < G; g++) {
                     if (tier) {
@@ -347,23 +368,11 @@ __global__ void __launch_bounds__(kThreads, MINB) k_scan(const __grid_constant__
                     }
                     const uint32_t dmin = min(min(d[0], d[1]), min(d[2], d[3]));
                     if (__any_sync(0xffffffffu, dmin <= hmax))
-                        emit_group(p, q0 + q, hmax, d[0], d[1], d[2], d[3], seg_id[g], row0[g], seg_n[g], s_rank, dirty - q0);
+                        emit_group(p, q0 + q, hmax, d[0], d[1], d[2], d[3], seg_id[g], row0[g], seg_n[g], s_rank, nullptr);
                 }
             }
         }
 
-        if (p.update_tau) {
-            __syncthreads();  // all emissions of this item are issued
-            __threadfence();
-            const uint32_t warp = tid >> 5, lane = tid & 31;
-            for (uint32_t q = warp; q < T; q += kThreads / 32) {
-                if (dirty[q]) {
-                    tighten_tau(p, q0 + q, lane);
-                    __syncwarp();
-                    if (lane == 0) dirty[q] = 0;
-                }
-            }
-        }
         b_lo = b_hi;
         item_blocks = min(item_blocks * 2, p.blocks_per_item);
     }
