@@ -260,6 +260,7 @@ struct LowerBound {
 template <int WE, int G, int MINB = 3>
 __global__ void __launch_bounds__(kThreads, MINB) k_scan(const __grid_constant__ ScanParams p) {
     constexpr int QW = (WE <= 4) ? 4 : 8;  // query words kept per query in shared memory
+    constexpr bool kInRec = WE < QW;       // a free word of the record carries the query's bound | tier: one address stream, no extra LDS
     extern __shared__ uint4 smem_raw[];
     const uint32_t tid = threadIdx.x;
     const uint32_t q0 = blockIdx.y * p.q_split;                 // first query of this CTA's sub-tile
@@ -305,9 +306,12 @@ __global__ void __launch_bounds__(kThreads, MINB) k_scan(const __grid_constant__
         const uint32_t b_hi = min(b_lo + item_blocks, my_hi);
         __syncthreads();  // previous item's readers of hm are done
         if (prefetch && n_items_done >= 3) {                  // steady state: bound fetched during the previous item
-            if (tid < T) hm[tid] = hm_next;
+            if (tid < T) { if (kInRec) qw[(size_t)tid * QW + QW - 1] = hm_next; else hm[tid] = hm_next; }
         } else {                                              // ramp-up items: always the freshest bound
-            for (uint32_t q = tid; q < T; q += kThreads) hm[q] = pack_bound(hrow[__ldcg(&p.tau[q0 + q])]);
+            for (uint32_t q = tid; q < T; q += kThreads) {
+                const uint16_t v = pack_bound(hrow[__ldcg(&p.tau[q0 + q])]);
+                if (kInRec) qw[(size_t)q * QW + QW - 1] = v; else hm[q] = v;
+            }
         }
         __syncthreads();
         if (prefetch && tid < T && p.update_tau) hm_next = pack_bound(hrow[__ldcg(&p.tau[q0 + tid])]);  // lands during the item
@@ -332,6 +336,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_scan(const __grid_constant__
 #pragma unroll 1
             for (uint32_t q = 0; q < T; q++) {
                 uint32_t qv[WE];
+                uint32_t hv;
                 {
                     const uint4* qp = reinterpret_cast<const uint4*>(qw + (size_t)q * QW);
                     uint4 v0 = qp[0];
@@ -339,15 +344,17 @@ __global__ void __launch_bounds__(kThreads, MINB) k_scan(const __grid_constant__
                     if (WE > 1) qv[1] = v0.y;
                     if (WE > 2) qv[2] = v0.z;
                     if (WE > 3) qv[3] = v0.w;
+                    hv = v0.w;
                     if (WE > 4) {
                         uint4 v1 = qp[1];
                         qv[4] = v1.x;
                         if (WE > 5) qv[5] = v1.y;
                         if (WE > 6) qv[6] = v1.z;
                         if (WE > 7) qv[7] = v1.w;
+                        hv = v1.w;
                     }
+                    if (!kInRec) hv = hm[q];
                 }
-                const uint32_t hv = hm[q];
                 const uint32_t hmax = hv & 0xfffu;
                 const uint32_t tier = hv >> 12;   // filter tier, uniform per query
 #pragma unroll

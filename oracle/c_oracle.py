@@ -123,5 +123,58 @@ def synth_topk(n_rows, seed, queries, qlens, k, lengths=(8, 16, 24, 32), key_mod
     return khi, klo, h, nb, counts
 
 
+class SoaStore:
+    """
+    The tuned CPU arm (oracle_soa_*): length-bucketed word planes + AVX-512 VPOPCNTDQ when the host CPU has it.
+    Same results as `topk`; used by bench.py's cpu_baseline / --impl reference legs and checked in tests/test_oracle.py.
+    """
+
+    def __init__(self, keys_hi, keys_lo, codes, lens):
+        L = lib()
+        L.oracle_soa_build.restype = ctypes.c_void_p
+        L.oracle_soa_build.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_size_t]
+        L.oracle_soa_free.argtypes = [ctypes.c_void_p]
+        L.oracle_soa_topk.restype = ctypes.c_int
+        L.oracle_soa_topk.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint32,
+                                      ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        lens = np.ascontiguousarray(lens, dtype=np.uint8)
+        keys_hi = np.ascontiguousarray(keys_hi, dtype=np.uint64)
+        keys_lo = None if keys_lo is None else np.ascontiguousarray(keys_lo, dtype=np.uint64)
+        self._h = L.oracle_soa_build(codes.ctypes.data, lens.ctypes.data, keys_hi.ctypes.data, None if keys_lo is None else keys_lo.ctypes.data, len(lens))
+        if not self._h:
+            raise ValueError("oracle_soa_build failed")
+
+    @staticmethod
+    def isa():
+        return "avx512-vpopcntdq" if lib().oracle_soa_isa() else "scalar popcnt"
+
+    def topk(self, queries, qlens, k, max_h_over_n=None, n_threads=0, force_scalar=False):
+        queries = np.ascontiguousarray(queries, dtype=np.uint8)
+        qlens = np.ascontiguousarray(qlens, dtype=np.uint8)
+        q = len(qlens)
+        rows = np.empty((q, k), dtype=np.int64)
+        h = np.empty((q, k), dtype=np.uint16)
+        nb = np.empty((q, k), dtype=np.uint16)
+        counts = np.empty(q, dtype=np.uint32)
+        tn, td = (0, 0) if max_h_over_n is None else max_h_over_n
+        rc = lib().oracle_soa_topk(self._h, queries.ctypes.data, qlens.ctypes.data, q, k, tn, td, rows.ctypes.data, h.ctypes.data,
+                                   nb.ctypes.data, counts.ctypes.data, n_threads, 1 if force_scalar else 0)
+        if rc != 0:
+            raise ValueError("oracle_soa_topk: bad arguments")
+        return rows, h, nb, counts
+
+    def close(self):
+        if self._h:
+            lib().oracle_soa_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def num_threads():
     return int(lib().oracle_num_threads())

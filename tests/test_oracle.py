@@ -163,3 +163,28 @@ def test_streaming_synth_topk_equals_in_memory_oracle():
         c = int(cnt[i])
         assert np.array_equal(skhi[i, :c], khi[rows[i, :c]]) and np.array_equal(sklo[i, :c], klo[rows[i, :c]])
         assert np.array_equal(sh[i, :c], h[i, :c])
+
+
+@pytest.mark.parametrize("force_scalar", [False, True])
+def test_tuned_cpu_arm_equals_the_plain_restatement(force_scalar):
+    """oracle_soa_topk (bucketed word planes, AVX-512 VPOPCNTDQ when present) is the timed CPU arm: same answers as `topk`."""
+    n, q, k = 60_000, 40, 37
+    lens = synth.make_lengths(0, n, 9, (5, 8, 16, 24, 32, 13))
+    codes = synth.make_codes(0, n, 9, lens)
+    keys = synth.make_keys(0, n, 9)
+    queries, qlens = synth.make_queries(q, n, 10, 9, lengths=(8, 16, 24, 32, 7), row_lengths=(5, 8, 16, 24, 32, 13))
+    want = c_oracle.topk(keys, None, codes, lens, queries, qlens, k)
+    st = c_oracle.SoaStore(keys, None, codes, lens)
+    got = st.topk(queries, qlens, k, n_threads=3, force_scalar=force_scalar)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    # threshold + 128-bit keys + duplicates
+    khi, klo, codes, lens = c_oracle.synth_rows(0, 30_000, 4, lengths=(8,), key_mode=1, dup_every=16, dup_back=65)
+    qs = codes[[14, 206, 4110, 999]].copy()
+    qs[3, 2] ^= 0x55
+    ql = np.full(4, 8, dtype=np.uint8)
+    for thr in ((0, 64), (16, 64), None):
+        want = c_oracle.topk(khi, klo, codes, lens, qs, ql, 50, thr)
+        got = c_oracle.SoaStore(khi, klo, codes, lens).topk(qs, ql, 50, thr, force_scalar=force_scalar)
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b)
