@@ -196,29 +196,29 @@ class B200Index:
                 rows = best.get(unit_type)
                 if not rows:
                     continue
-                old = self._nphd_indexes.pop(unit_type, None)
-                if old is not None:
-                    old.reset()
-                    old.close()
+                # the old store keeps answering searches from HBM until the new one is swapped in; closing it waits for
+                # the searches still running on it (isx_close takes the store's locks)
+                old = self._nphd_indexes.get(unit_type)
                 shutil.rmtree(self.path / unit_type, ignore_errors=True)
                 index = self._stores.nphd(self.max_dim, self.path / unit_type)
                 index.add(list(rows.keys()), list(rows.values()))
                 index.save()
                 self._nphd_indexes[unit_type] = index
+                if old is not None:
+                    old.close()
                 rebuilt_units.append(unit_type)
             for sp_type in simprint_types:
                 keys, vectors = self._simprint_rows(sp_type)
                 if not keys:
                     continue
-                old = self._simprint_indexes.pop(sp_type, None)
-                if old is not None:
-                    old.reset()
-                    old.close()
+                old = self._simprint_indexes.get(sp_type)
                 shutil.rmtree(self.path / f"SIMPRINT_{sp_type}", ignore_errors=True)
                 index = self._stores.simprint(self.path / f"SIMPRINT_{sp_type}", 8 * len(vectors[0]), self._opts["oversampling_factor"])
                 index.add_raw(keys, vectors)
                 index.save()
                 self._simprint_indexes[sp_type] = index
+                if old is not None:
+                    old.close()
                 rebuilt_sp.append(sp_type)
             return {"unit_types": rebuilt_units, "simprint_types": rebuilt_sp}
 
@@ -249,25 +249,16 @@ class B200Index:
         schema = entries.schema
         results = []
         with self._write_lock:
-            if self._realm_id is None:  # inferred from the first asset (index.py:239-252)
+            # Everything that can reject an asset runs BEFORE the first mutation of the log or a store: ids, realm,
+            # unit codes, simprint base64 and chunk-pointer limits are decoded here once and only the decoded values
+            # are used below. The reference gets the same all-or-nothing behaviour from its LMDB write transaction.
+            realm = self._realm_id
+            if realm is None:  # inferred from the first asset (index.py:239-252); adopted once the batch is accepted
                 if assets[0].iscc_id is None:
                     raise ValueError("Asset must have iscc_id field when adding to index")
-                self._realm_id = entries.extract_realm_id(assets[0].iscc_id)  # persisted below, once the batch is accepted
-
-            # validate the whole batch before the first mutation (the reference's LMDB transaction would roll back)
-            for asset in assets:
-                if asset.iscc_id is None:
-                    raise ValueError("Asset must have iscc_id field when adding to index")
-                asset_realm = entries.extract_realm_id(asset.iscc_id)
-                if self._realm_id != asset_realm:
-                    raise ValueError(
-                        f"Realm ID mismatch: index has realm={self._realm_id}, "
-                        f"but asset '{asset.iscc_id}' has realm={asset_realm}. "
-                        f"All assets in an index must have the same realm ID."
-                    )
-                for unit_str in asset.units or []:
-                    IsccUnit(unit_str).unit_type
-
+                realm = entries.extract_realm_id(assets[0].iscc_id)
+            prepared = [self._prepare_asset(asset, realm) for asset in assets]
+            self._realm_id = realm
             if self._log.realm_id != self._realm_id:
                 self._log.set_realm(self._realm_id)
 
@@ -279,9 +270,8 @@ class B200Index:
             last_occurrence = {asset.iscc_id: i for i, asset in enumerate(assets)}  # in-batch dedup, last wins (:263-265)
             batch_seen = set()
 
-            for i, asset in enumerate(assets):
-                iscc_id_obj = IsccID(asset.iscc_id)
-                key = int(iscc_id_obj)
+            for i, (asset, prep) in enumerate(zip(assets, prepared)):
+                key, iscc_id_body = prep["key"], prep["body"]
                 existing = self._log.assets.get(key)
                 status = schema.Status.updated if (existing or key in batch_seen) else schema.Status.created
                 batch_seen.add(key)
@@ -289,9 +279,8 @@ class B200Index:
                     results.append(schema.IsccAddResult(iscc_id=asset.iscc_id, status=status))
                     continue
 
-                asset_bytes = entries.serialize_asset(asset)
-                iscc_id_body = iscc_id_obj.body
-                sp_fingerprints = {t: simprint_fingerprint(lst) for t, lst in (asset.simprints or {}).items()}
+                asset_bytes = prep["bytes"]
+                sp_fingerprints = prep["fingerprints"]
                 # idempotent re-add: nothing to do when stored bytes, derived unit rows and simprints are all current (:294-327)
                 if (existing == asset_bytes and self._nphd_units_present(key, asset.units)
                         and self._simprints_already_indexed(iscc_id_body, asset, sp_fingerprints)):
@@ -309,29 +298,25 @@ class B200Index:
 
                 self._log.put_asset(key, asset_bytes)
 
-                for unit_str in asset.units or []:
-                    unit = IsccUnit(unit_str)
-                    if unit.unit_type.startswith("INSTANCE_"):
-                        instance_add.append((key, unit.body))
+                for unit_type, body in prep["units"]:
+                    if unit_type.startswith("INSTANCE_"):
+                        instance_add.append((key, body))
                     else:
-                        batch = nphd_batches.setdefault(unit.unit_type, ([], []))
+                        batch = nphd_batches.setdefault(unit_type, ([], []))
                         batch[0].append(key)
-                        batch[1].append(unit.body)
+                        batch[1].append(body)
 
-                for sp_type, sp_list in (asset.simprints or {}).items():
+                for sp_type, rows in prep["simprints"].items():
                     table = self._log.simprints.get(sp_type) or {}
                     if iscc_id_body in table:  # update: old chunk pointers leave the derived store (:379-383)
                         old_entries = table[iscc_id_body][1]
                         sp_deleted_keys.setdefault(sp_type, []).extend(
                             pack_chunk_pointer(iscc_id_body, o, z) for _s, o, z in old_entries)
-                    new_entries = []
                     batch = sp_batches.setdefault(sp_type, ([], []))
-                    for sp_obj in sp_list:
-                        sp_bytes = ic.decode_base64(sp_obj.simprint)
-                        new_entries.append((sp_bytes, sp_obj.offset, sp_obj.size))
-                        batch[0].append(pack_chunk_pointer(iscc_id_body, sp_obj.offset, sp_obj.size))
+                    for sp_bytes, _offset, _size, pointer in rows:
+                        batch[0].append(pointer)
                         batch[1].append(np.frombuffer(sp_bytes, dtype=np.uint8))
-                    self._log.put_simprints(sp_type, iscc_id_body, sp_fingerprints[sp_type], new_entries)
+                    self._log.put_simprints(sp_type, iscc_id_body, sp_fingerprints[sp_type], [r[:3] for r in rows])
 
                 results.append(schema.IsccAddResult(iscc_id=asset.iscc_id, status=status))
 
@@ -364,6 +349,37 @@ class B200Index:
                     if index.dirty >= flush_interval:
                         index.save()
         return results
+
+    def _prepare_asset(self, asset, realm):
+        # type: (object, int) -> dict
+        """Decode one incoming asset completely (raises ValueError on anything malformed); nothing is stored here."""
+        if asset.iscc_id is None:
+            raise ValueError("Asset must have iscc_id field when adding to index")
+        asset_realm = entries.extract_realm_id(asset.iscc_id)
+        if realm != asset_realm:
+            raise ValueError(
+                f"Realm ID mismatch: index has realm={realm}, "
+                f"but asset '{asset.iscc_id}' has realm={asset_realm}. "
+                f"All assets in an index must have the same realm ID."
+            )
+        iscc_id_obj = IsccID(asset.iscc_id)
+        body = iscc_id_obj.body
+        units = []
+        for unit_str in asset.units or []:
+            unit = IsccUnit(unit_str)
+            units.append((unit.unit_type, unit.body))
+        simprints, fingerprints = {}, {}
+        for sp_type, sp_list in (asset.simprints or {}).items():
+            rows = []
+            for sp_obj in sp_list:
+                sp_bytes = ic.decode_base64(sp_obj.simprint)
+                rows.append((sp_bytes, sp_obj.offset, sp_obj.size, pack_chunk_pointer(body, sp_obj.offset, sp_obj.size)))
+            if rows and len({len(r[0]) for r in rows}) != 1:
+                raise ValueError(f"Simprints of type '{sp_type}' in asset '{asset.iscc_id}' have different lengths")
+            simprints[sp_type] = rows
+            fingerprints[sp_type] = simprint_fingerprint(sp_list)
+        return {"key": int(iscc_id_obj), "body": body, "bytes": entries.serialize_asset(asset), "units": units,
+                "simprints": simprints, "fingerprints": fingerprints}
 
     def _nphd_units_present(self, key, units):
         for unit_str in units or []:

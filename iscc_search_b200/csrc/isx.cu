@@ -14,6 +14,7 @@
 #include <numeric>
 #include <shared_mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/isx.h"
@@ -1050,9 +1051,14 @@ static void free_rows(isx_store* s) {
 
 int isx_close(isx_store_t* s) {
     if (!s) return 0;
-    cudaSetDevice(s->device);
-    cudaStreamSynchronize(s->stream);
-    free_rows(s);
+    {   // wait for searches / mutations in flight on other threads (they hold rows_mu shared or work_mu); a call that
+        // arrives after this point is a use-after-close of the caller, as with any handle
+        std::unique_lock<std::shared_mutex> g(s->rows_mu);
+        std::lock_guard<std::mutex> gw(s->work_mu);
+        cudaSetDevice(s->device);
+        cudaStreamSynchronize(s->stream);
+        free_rows(s);
+    }
     DevBuf* bufs[] = {&s->d_segs, &s->d_blocks, &s->tables.d_rank, &s->tables.d_hmax, &s->d_stage_codes, &s->d_stage_keys,
                       &s->d_stage_dest, &s->d_moves, &s->d_queries, &s->d_tau, &s->d_hist, &s->d_shist, &s->d_cnt, &s->d_ovf, &s->d_cand,
                       &s->d_qmap, &s->d_fb, &s->d_fb_cand, &s->d_out_khi, &s->d_out_klo, &s->d_out_h, &s->d_out_n,
@@ -1152,6 +1158,11 @@ int isx_add(isx_store_t* s, const void* keys, const uint8_t* codes, const uint8_
         if (L < 1 || L > s->max_bytes) return fail(ISX_EINVAL, "row %zu: code length %u bytes outside 1..%u", i, L, s->max_bytes);
         if (s->fixed_len && L != s->fixed_len) return fail(ISX_EINVAL, "row %zu: code length %u bytes, index expects %u", i, L, s->fixed_len);
     }
+    // staging buffers first: an allocation failure must not leave the key map ahead of the device rows
+    {
+        const size_t cn0 = std::min<size_t>((size_t)4 << 20, n);
+        if (s->d_stage_codes.ensure(cn0 * 32) || s->d_stage_keys.ensure(cn0 * s->key_bytes) || s->d_stage_dest.ensure(cn0 * 8)) return ISX_ENOMEM;
+    }
     s->map.reserve(s->map.size() + n);
     // rows needed per bucket (upper bound: duplicates are skipped later) so big batches get big segments
     uint64_t need[kMaxBytes + 1] = {0};
@@ -1221,7 +1232,10 @@ int isx_remove(isx_store_t* s, const void* keys, size_t n, uint8_t* removed, uin
     int rc = set_device(s);
     if (rc) return rc;
     if ((rc = sync_map(s))) return rc;
-    std::vector<uint4> moves;
+    // Swap-remove on the host mirrors, one key at a time; the device copies are deferred: `origin` maps a row that now
+    // holds moved data to the ORIGINAL location of that data, so a chain (row moved into a hole, hole removed again
+    // later in the batch) collapses to one net move - or to none when the moved row was removed as well.
+    std::unordered_map<uint64_t, uint64_t> origin;
     uint64_t cnt = 0;
     for (size_t i = 0; i < n; i++) {
         Key128 key = load_key(s, keys, i);
@@ -1236,14 +1250,19 @@ int isx_remove(isx_store_t* s, const void* keys, size_t n, uint8_t* removed, uin
         uint32_t lsid = bs[li - 1];
         Segment& last = s->segs[lsid];
         uint32_t lrow = last.desc.n - 1;
+        const uint64_t last_loc = ((uint64_t)lsid << 32) | lrow;
         s->map.erase(key);
-        if (!(lsid == sid && lrow == row)) {
+        origin.erase(loc);   // whatever was moved here before is gone now
+        if (last_loc != loc) {
             Key128 moved{last.h_khi[lrow], s->key_bytes == 16 ? last.h_klo[lrow] : 0};
             Segment& dst = s->segs[sid];
             dst.h_khi[row] = moved.hi;
             if (s->key_bytes == 16) dst.h_klo[row] = moved.lo;
-            s->map.update(moved, ((uint64_t)sid << 32) | row);
-            moves.push_back(make_uint4(sid, row, lsid, lrow));
+            s->map.update(moved, loc);
+            auto it = origin.find(last_loc);
+            const uint64_t src = it == origin.end() ? last_loc : it->second;
+            if (it != origin.end()) origin.erase(it);
+            origin[loc] = src;
         }
         last.desc.n--;
         last.mirrored = last.desc.n;
@@ -1254,13 +1273,17 @@ int isx_remove(isx_store_t* s, const void* keys, size_t n, uint8_t* removed, uin
     }
     if (n_removed) *n_removed = cnt;
     if (cnt == 0) return 0;
+    std::vector<uint4> moves;
+    moves.reserve(origin.size());
+    for (const auto& kv : origin)
+        moves.push_back(make_uint4((uint32_t)(kv.first >> 32), (uint32_t)kv.first, (uint32_t)(kv.second >> 32), (uint32_t)kv.second));
     s->segs_dirty = true;
     s->version++;
     if ((rc = upload_segs(s))) return rc;
     if (!moves.empty()) {
         if (s->d_moves.ensure(moves.size() * sizeof(uint4))) return ISX_ENOMEM;
         CU(cudaMemcpyAsync(s->d_moves.p, moves.data(), moves.size() * sizeof(uint4), cudaMemcpyHostToDevice, s->stream));
-        k_move_rows<<<1, 32, 0, s->stream>>>(s->d_segs.as<SegDesc>(), s->d_moves.as<uint4>(), moves.size());
+        k_move_rows<<<(unsigned)((moves.size() * 32 + 255) / 256), 256, 0, s->stream>>>(s->d_segs.as<SegDesc>(), s->d_moves.as<uint4>(), moves.size());
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(s->stream));
     }

@@ -975,19 +975,19 @@ __global__ void k_synth_rows(const __grid_constant__ SynthParams g, size_t n, ui
     }
 }
 
-// Ordered row moves of swap-remove: move[i] = (dst seg, dst row, src seg, src row); one warp walks
-// the list in order (moves may chain), lane w copies word w.
+// Row moves of a batch of swap-removes: move[i] = (dst seg, dst row, src seg, src row). The host resolves chains
+// (a row moved into a hole that is removed later in the same batch) to NET moves first: every source is a row beyond the
+// bucket's final size, every destination a live row below it, so the moves are independent - one warp each, lane w
+// copies word w, lanes 8 and 9 the key halves. A bulk update of 10^5 assets is one launch of 10^5 warps.
 __global__ void k_move_rows(const SegDesc* segs, const uint4* moves, size_t n) {
-    const uint32_t lane = threadIdx.x;
-    for (size_t i = 0; i < n; i++) {
-        uint4 mv = moves[i];
-        const SegDesc d = segs[mv.x], s = segs[mv.z];
-        if (lane < d.words) d.planes[(size_t)lane * d.cap + mv.y] = s.planes[(size_t)lane * s.cap + mv.w];
-        if (lane == 8) d.khi[mv.y] = s.khi[mv.w];
-        if (lane == 9 && d.klo) d.klo[mv.y] = s.klo[mv.w];
-        __syncwarp();
-        __threadfence_block();
-    }
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const uint4 mv = moves[i];
+    const SegDesc d = segs[mv.x], s = segs[mv.z];
+    if (lane < d.words) d.planes[(size_t)lane * d.cap + mv.y] = s.planes[(size_t)lane * s.cap + mv.w];
+    if (lane == 8) d.khi[mv.y] = s.khi[mv.w];
+    if (lane == 9 && d.klo) d.klo[mv.y] = s.klo[mv.w];
 }
 
 // Simprint grouping on the device: per query, flag the FIRST (= best, lists are sorted) record of

@@ -31,13 +31,18 @@ class InstancePrefixIndex:
     def __init__(self, device=0, store=None):
         self._store = store if store is not None else _default_store(device)
 
-    @staticmethod
-    def _key(iscc_id_key, code):
-        # (ISCC-ID, body) pairs are unique in the dupsort table (index.py:365-366, dupdata=False): the row key is the
-        # ISCC-ID followed by the body length and a 56-bit digest of the body
-        return struct.pack(">QB", int(iscc_id_key), len(code)) + hashlib.blake2b(code, digest_size=7).digest()
+    MAX_SLOTS = 256
 
-    def _rows(self, pairs):
+    @staticmethod
+    def _key(iscc_id_key, code, slot=0):
+        # (ISCC-ID, body) pairs are unique in the dupsort table (index.py:365-366, dupdata=False). The 16-byte row key is
+        # ISCC-ID | body length | 48-bit digest of the body | slot. The digest only spreads the bodies of one asset over
+        # key space; identity is decided by the stored body itself: `_locate` compares it and walks the slot byte when two
+        # different bodies of one asset and length share a digest, so no row is ever dropped or confused (exact, not
+        # probabilistic).
+        return struct.pack(">QB", int(iscc_id_key), len(code)) + hashlib.blake2b(code, digest_size=6).digest() + bytes([slot])
+
+    def _rows(self, pairs, slots=None):
         n = len(pairs)
         keys = np.zeros((n, 16), dtype=np.uint8)
         codes = np.zeros((n, 32), dtype=np.uint8)
@@ -46,10 +51,35 @@ class InstancePrefixIndex:
             code = bytes(code)
             if not 1 <= len(code) <= 32:
                 raise ValueError(f"INSTANCE body must be 1..32 bytes, got {len(code)}")
-            keys[i] = np.frombuffer(self._key(iscc_id_key, code), dtype=np.uint8)
+            keys[i] = np.frombuffer(self._key(iscc_id_key, code, 0 if slots is None else slots[i]), dtype=np.uint8)
             codes[i, : len(code)] = np.frombuffer(code, dtype=np.uint8)
             lens[i] = len(code)
         return keys, codes, lens
+
+    def _locate(self, pairs):
+        # type: (list[tuple[int, bytes]]) -> tuple[list[int], list[bool]]
+        """Per pair: (slot, present) - the slot that holds exactly this body, or the first free slot of its digest chain."""
+        slots, present = [0] * len(pairs), [False] * len(pairs)
+        todo = list(range(len(pairs)))
+        for slot in range(self.MAX_SLOTS):
+            if not todo:
+                break
+            sub = [pairs[i] for i in todo]
+            keys, codes, lens = self._rows(sub, [slot] * len(sub))
+            got_codes, got_lens = self._store.get(keys, len(sub))
+            nxt = []
+            for j, i in enumerate(todo):
+                slots[i] = slot
+                if got_lens[j] == 0:
+                    continue                                   # free slot: the body is not stored
+                if got_lens[j] == lens[j] and np.array_equal(got_codes[j], codes[j]):
+                    present[i] = True                          # this very body
+                else:
+                    nxt.append(i)                              # digest collision with another body: next slot
+            todo = nxt
+        if todo:
+            raise ValueError("INSTANCE digest chain exhausted")   # 256 bodies of one asset and length with one 48-bit digest
+        return slots, present
 
     def add(self, iscc_id_key, instance_code):
         # type: (int, bytes) -> None
@@ -59,8 +89,23 @@ class InstancePrefixIndex:
     def add_many(self, pairs):
         # type: (list[tuple[int, bytes]]) -> None
         """One batched add of (ISCC-ID key, body) pairs; pairs already present are skipped (dupdata=False)."""
-        if pairs:
-            self._store.add(*self._rows(pairs))
+        if not pairs:
+            return
+        pairs = list(dict.fromkeys((int(k), bytes(c)) for k, c in pairs))   # in-batch duplicates collapse
+        slots, present = self._locate(pairs)
+        new = [i for i in range(len(pairs)) if not present[i]]
+        first_of_chain, later = {}, []
+        for i in new:   # bodies of one batch that share a digest chain go in one after the other (never happens in practice)
+            chain = self._key(*pairs[i])[:15]
+            if chain in first_of_chain:
+                later.append(i)
+            else:
+                first_of_chain[chain] = i
+        new = list(first_of_chain.values())
+        if new:
+            self._store.add(*self._rows([pairs[i] for i in new], [slots[i] for i in new]))
+        for i in later:
+            self.add_many([pairs[i]])
 
     def remove(self, iscc_id_key, instance_code):
         # type: (int, bytes) -> int
@@ -71,8 +116,27 @@ class InstancePrefixIndex:
         # type: (list[tuple[int, bytes]]) -> int
         if not pairs:
             return 0
-        keys, _codes, _lens = self._rows(pairs)
-        return self._store.remove(keys, len(keys))[1]
+        pairs = list(dict.fromkeys((int(k), bytes(c)) for k, c in pairs))
+        slots, present = self._locate(pairs)
+        hit = [i for i in range(len(pairs)) if present[i]]
+        if not hit:
+            return 0
+        keys, _codes, _lens = self._rows([pairs[i] for i in hit], [slots[i] for i in hit])
+        removed = self._store.remove(keys, len(keys))[1]
+        # keep digest chains gap-free (lookups stop at the first free slot): a body stored behind a removed one moves up
+        for i in hit:
+            key_id, code = pairs[i]
+            slot = slots[i]
+            while slot + 1 < self.MAX_SLOTS:
+                nxt = np.frombuffer(self._key(key_id, code, slot + 1), dtype=np.uint8).reshape(1, 16).copy()
+                got_codes, got_lens = self._store.get(nxt, 1)
+                if got_lens[0] == 0:
+                    break
+                self._store.remove(nxt, 1)
+                moved = np.frombuffer(self._key(key_id, code, slot), dtype=np.uint8).reshape(1, 16).copy()
+                self._store.add(moved, got_codes[:1].copy(), got_lens[:1].copy())
+                slot += 1
+        return removed
 
     def search(self, instance_code):
         # type: (bytes) -> dict[int, float]

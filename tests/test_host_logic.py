@@ -62,3 +62,32 @@ def test_device_arithmetic_helpers_on_the_host():
     for seed in (1, 2, 3):
         rc = L.isx_selftest_distance(20_000, seed)
         assert rc == 0, L.isx_last_error()
+
+
+def test_instance_index_digest_collisions_never_lose_a_row(cpu_stores, monkeypatch):
+    """Two different bodies of one asset whose digests collide occupy consecutive slots; removal keeps the chain gap-free."""
+    import hashlib
+
+    from iscc_search_b200.instance import InstancePrefixIndex
+
+    real = hashlib.blake2b
+
+    class Colliding:
+        def __init__(self, data, digest_size):
+            self._d = bytes([7]) * digest_size   # every body gets the same digest
+
+        def digest(self):
+            return self._d
+
+    idx = InstancePrefixIndex(store=cpu_stores(0, 16, 32, 0))
+    monkeypatch.setattr("iscc_search_b200.instance.hashlib.blake2b", Colliding)
+    a, b, c = bytes(range(8)), bytes(range(8, 16)), bytes(range(16, 24))
+    idx.add_many([(5, a), (5, b), (5, c), (5, a)])
+    assert len(idx) == 3
+    assert idx.search(a) == {5: 1.0} and idx.search(b) == {5: 1.0} and idx.search(c) == {5: 1.0}
+    assert idx.remove(5, a) == 1 and len(idx) == 2          # head of the chain goes, the others move up
+    idx.add(5, b)                                            # still found: no duplicate row
+    assert len(idx) == 2
+    assert idx.remove(5, c) == 1 and idx.remove(5, c) == 0
+    assert idx.search(b) == {5: 1.0} and idx.search(c) == {} and idx.search(a) == {}
+    monkeypatch.setattr("iscc_search_b200.instance.hashlib.blake2b", real)
