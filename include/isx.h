@@ -182,6 +182,18 @@ int isx_match_all(isx_store_t* s, const uint8_t* query, uint32_t qlen, uint32_t 
                   void* keys_out, uint16_t* hamming_out, uint16_t* nbits_out, uint64_t* total_out);
 
 /*
+ * Simprint asset scoring on the device (the per-asset loop of iscc_search/indexes/simprint/usearch_core.py:199-269):
+ * the best record of every (asset, query simprint) pair, grouped by asset (segment a = records [seg[a], seg[a+1])),
+ * ascending query index inside a segment: rec_qi (query index), rec_sim (1 - h/ndim), rec_idf (IDF of the matched
+ * simprint); q_idf[q] = IDF of query simprint q (added for every query the asset did not match).
+ * score_out[a] = sum(idf * sim) / (sum(idf of matched) + sum(idf of unmatched queries)), every double operation in the
+ * reference's order and rounding (no FMA), so the result is bit-identical to the reference's Python floats.
+ * All pointers are host pointers.
+ */
+int isx_score_segments(isx_store_t* s, const uint32_t* seg, size_t n_assets, const uint32_t* rec_qi, const double* rec_sim,
+                       const double* rec_idf, size_t n_rec, const double* q_idf, uint32_t n_queries, double* score_out);
+
+/*
  * Cross-rank threshold sharing for row-sharded search (one process per GPU, all GPUs on one NVLink box).
  * Every rank owns "home" rank-histograms for a slice of the queries of a batch; peers map them through
  * CUDA IPC and (a) count every candidate they emit there with remote atomics, (b) tighten their thresholds

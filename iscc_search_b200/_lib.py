@@ -50,7 +50,7 @@ SYMBOLS = (
     "isx_last_error", "isx_abi_version", "isx_device_count", "isx_open", "isx_close", "isx_set_stream",
     "isx_set_profiling", "isx_get_stats", "isx_add", "isx_add_device", "isx_synth_rows_device", "isx_remove", "isx_contains", "isx_get", "isx_size",
     "isx_clear", "isx_device_bytes", "isx_length_mask", "isx_save", "isx_load", "isx_search",
-    "isx_search_device", "isx_merge_device", "isx_max_k", "isx_match_all", "isx_share_init", "isx_share_attach",
+    "isx_search_device", "isx_merge_device", "isx_max_k", "isx_match_all", "isx_score_segments", "isx_share_init", "isx_share_attach",
     "isx_share_reset", "isx_share_set_lengths", "isx_selftest_rank_table", "isx_selftest_keymap", "isx_selftest_distance",
 )
 
@@ -107,6 +107,7 @@ def lib():
     L.isx_merge_device.argtypes = [vp, u32, sz, u32, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci]
     L.isx_max_k.argtypes = [vp, P(u32)]
     L.isx_match_all.argtypes = [vp, vp, u32, u32, u32, sz, vp, vp, vp, P(u64)]
+    L.isx_score_segments.argtypes = [vp, vp, sz, vp, vp, vp, sz, vp, u32, vp]
     L.isx_share_init.argtypes = [vp, u32, u32, u32, vp]
     L.isx_share_attach.argtypes = [vp, u32, vp]
     L.isx_share_reset.argtypes = [vp]
@@ -255,6 +256,20 @@ class Store:
         check(lib().isx_search(self.handle, ptr(queries), ptr(qlens), q, k, tn, td, ptr(keys), ptr(h), ptr(nb), ptr(counts), ptr(codes),
                                ptr(first_of_asset)))
         return keys, h, nb, counts, codes
+
+    def score_segments(self, seg, rec_qi, rec_sim, rec_idf, q_idf):
+        # type: (np.ndarray, np.ndarray, np.ndarray, np.ndarray, np.ndarray) -> np.ndarray
+        """Per-asset IDF-weighted simprint scores on the device (include/isx.h: isx_score_segments)."""
+        seg = np.ascontiguousarray(seg, dtype=np.uint32)
+        rec_qi = np.ascontiguousarray(rec_qi, dtype=np.uint32)
+        rec_sim = np.ascontiguousarray(rec_sim, dtype=np.float64)
+        rec_idf = np.ascontiguousarray(rec_idf, dtype=np.float64)
+        q_idf = np.ascontiguousarray(q_idf, dtype=np.float64)
+        n_assets = len(seg) - 1
+        out = np.zeros(n_assets, dtype=np.float64)
+        check(lib().isx_score_segments(self.handle, ptr(seg), n_assets, ptr(rec_qi), ptr(rec_sim), ptr(rec_idf), len(rec_qi), ptr(q_idf),
+                                       len(q_idf), ptr(out)))
+        return out
 
     def match_all(self, query, thr=(0, 1), max_out=4096):
         # type: (bytes, tuple[int,int], int) -> tuple

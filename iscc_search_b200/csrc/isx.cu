@@ -872,7 +872,10 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
         // sub-tiles (gridDim.y) to fill the chip; every range is scanned exactly once.
         uint32_t done = 0;
         if (T >= 64) {
-            for (uint32_t span : {64u, 512u}) {
+            // with shared thresholds all ranks warm up at once on `world` times the rows: each rank's share of the two
+            // ranges shrinks accordingly (the ranges run at low occupancy, 5 % of a 12.5 M-row shard otherwise)
+            const uint32_t w = share_on ? s->share_world : 1;
+            for (uint32_t span : {std::max(8u, 64u / w), std::max(64u, 512u / w)}) {
                 if (n_blocks_total - done <= span * 4) break;
                 if ((rc = scan_range(s, p, done, done + span, bpi_main, lane))) return rc;
                 done += span;
@@ -1634,6 +1637,36 @@ int isx_match_all(isx_store_t* s, const uint8_t* query, uint32_t qlen, uint32_t 
     CU(cudaStreamSynchronize(s->stream));
     if (s->key_bytes == 8) memcpy(keys_out, khi.data(), (size_t)n * 8);
     else for (uint32_t i = 0; i < n; i++) store_key(s, keys_out, i, khi[i], klo[i]);
+    return 0;
+}
+
+int isx_score_segments(isx_store_t* s, const uint32_t* seg, size_t n_assets, const uint32_t* rec_qi, const double* rec_sim,
+                       const double* rec_idf, size_t n_rec, const double* q_idf, uint32_t n_queries, double* score_out) {
+    if (!s) return fail(ISX_EINVAL, "store is NULL");
+    if (n_assets == 0) return 0;
+    if (!seg || !rec_qi || !rec_sim || !rec_idf || !q_idf || !score_out) return fail(ISX_EINVAL, "NULL argument");
+    if (n_assets > 0xfffffff0u || n_rec > 0xfffffff0u) return fail(ISX_ELIMIT, "too many records");
+    std::lock_guard<std::mutex> gw(s->work_mu);
+    int rc = set_device(s);
+    if (rc) return rc;
+    // one staging block: seg | qi | sim | idf | q_idf | score
+    const size_t b_seg = (n_assets + 1) * 4, b_qi = n_rec * 4, b_d = n_rec * 8, b_q = (size_t)n_queries * 8, b_out = n_assets * 8;
+    auto al = [](size_t x) { return (x + 15) / 16 * 16; };
+    const size_t o_qi = al(b_seg), o_sim = o_qi + al(b_qi), o_idf = o_sim + al(b_d), o_q = o_idf + al(b_d), o_out = o_q + al(b_q);
+    if (s->d_stage_codes.ensure(o_out + b_out)) return ISX_ENOMEM;
+    uint8_t* d = s->d_stage_codes.as<uint8_t>();
+    CU(cudaMemcpyAsync(d, seg, b_seg, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(d + o_qi, rec_qi, b_qi, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(d + o_sim, rec_sim, b_d, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(d + o_idf, rec_idf, b_d, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(d + o_q, q_idf, b_q, cudaMemcpyHostToDevice, s->stream));
+    k_score_segments<<<(unsigned)((n_assets + 127) / 128), 128, 0, s->stream>>>(
+        reinterpret_cast<const uint32_t*>(d), reinterpret_cast<const uint32_t*>(d + o_qi), reinterpret_cast<const double*>(d + o_sim),
+        reinterpret_cast<const double*>(d + o_idf), reinterpret_cast<const double*>(d + o_q), (uint32_t)n_assets, n_queries,
+        reinterpret_cast<double*>(d + o_out));
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(score_out, d + o_out, b_out, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
     return 0;
 }
 

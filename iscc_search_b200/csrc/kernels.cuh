@@ -1029,6 +1029,33 @@ __global__ void k_first_per_asset(const uint64_t* khi, const uint32_t* cnt, uint
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Simprint asset scoring: the IDF-weighted similarity of usearch_core.py:199-269 as a segmented
+// reduce. Input: the best record of every (asset, query simprint) pair, grouped by asset, ascending query index inside
+// an asset - rec_qi / rec_sim / rec_idf, segment a = records [seg[a], seg[a+1]). One thread per asset walks its segment
+// in order and then the query simprints the asset did NOT match, exactly the order in which the reference's Python
+// adds the terms; every operation is an explicitly rounded IEEE double (__dadd_rn / __dmul_rn / __ddiv_rn: no FMA
+// contraction), so the scores are bit-identical to the reference's floats.
+__global__ void k_score_segments(const uint32_t* __restrict__ seg, const uint32_t* __restrict__ rec_qi, const double* __restrict__ rec_sim,
+                                 const double* __restrict__ rec_idf, const double* __restrict__ q_idf, uint32_t n_assets, uint32_t S,
+                                 double* __restrict__ score) {
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n_assets) return;
+    const uint32_t lo = seg[a], hi = seg[a + 1];
+    double total = 0.0, weighted = 0.0;
+    for (uint32_t i = lo; i < hi; i++) {          // matched query simprints, ascending query index
+        const double idf = rec_idf[i];
+        total = __dadd_rn(total, idf);
+        weighted = __dadd_rn(weighted, __dmul_rn(idf, rec_sim[i]));
+    }
+    uint32_t i = lo;
+    for (uint32_t q = 0; q < S; q++) {            // then every query simprint without a match (coverage penalty)
+        if (i < hi && rec_qi[i] == q) { i++; continue; }
+        total = __dadd_rn(total, q_idf[q]);
+    }
+    score[a] = total > 0.0 ? __ddiv_rn(weighted, total) : 0.0;
+}
+
 // queries (device, caller order) -> group order: dst[i] = src[order[i]], 32 bytes per query, bytes beyond the
 // query's length zeroed (8 threads per query, one word each)
 __global__ void k_gather_queries(const uint32_t* src, const uint32_t* order, const uint8_t* qlens_sorted, uint32_t* dst, uint32_t Q) {

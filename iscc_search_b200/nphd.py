@@ -250,6 +250,10 @@ class ShardedIndex128(_IndexBase):
         self.ndim = ndim
         self._init_store(path, ndim // 8, ndim // 8, device)
 
+    def score_segments(self, seg, rec_qi, rec_sim, rec_idf, q_idf):
+        """Per-asset simprint scores on this index's device (include/isx.h: isx_score_segments)."""
+        return self._store.score_segments(seg, rec_qi, rec_sim, rec_idf, q_idf)
+
     def _normalize_batch_keys(self, keys):
         # type: (object) -> np.ndarray
         """list of 16-byte keys (or array) -> structured-free `V16` array (one row per key), usearch_core.py:100."""
@@ -505,6 +509,10 @@ class MultiDeviceIndex128:
 
     _normalize_batch_keys = ShardedIndex128._normalize_batch_keys
     _raw_keys = ShardedIndex128._raw_keys
+
+    def score_segments(self, seg, rec_qi, rec_sim, rec_idf, q_idf):
+        """Per-asset simprint scores (pure arithmetic on host-provided records): any of the devices will do."""
+        return self.shards[0].score_segments(seg, rec_qi, rec_sim, rec_idf, q_idf)
 
     def _owner(self, raw_keys):
         from iscc_search_b200.sharded import owner_of

@@ -18,6 +18,22 @@ class OracleStore:
         self.rows = {}  # key (int | bytes16) -> code bytes, insertion ordered
         self.launches = 0
 
+    def score_segments(self, seg, rec_qi, rec_sim, rec_idf, q_idf):
+        """Test double of isx_score_segments: the same sums as plain Python floats (left to right, no compensation)."""
+        out = np.zeros(len(seg) - 1, dtype=np.float64)
+        for a in range(len(seg) - 1):
+            total, weighted = 0.0, 0.0
+            matched = set()
+            for i in range(int(seg[a]), int(seg[a + 1])):
+                total += float(rec_idf[i])
+                weighted += float(rec_idf[i]) * float(rec_sim[i])
+                matched.add(int(rec_qi[i]))
+            for q in range(len(q_idf)):
+                if q not in matched:
+                    total += float(q_idf[q])
+            out[a] = weighted / total if total > 0 else 0.0
+        return out
+
     # -- helpers
     def _key(self, keys, i):
         return int(keys[i]) if self.key_bytes == 8 else bytes(np.asarray(keys[i], dtype=np.uint8).tobytes())

@@ -14,7 +14,7 @@ import pytest
 from iscc_search_b200 import BatchMatches, Matches, ShardedIndex128, ShardedNphdIndex, synth
 from iscc_search_b200._lib import Store
 from oracle.nphd_oracle import StoreOracle
-from tests.helpers import assert_same_topk, oracle_topk
+from tests.helpers import assert_same_topk, make_store_arrays, oracle_topk
 
 pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).parent / "golden"
@@ -224,4 +224,37 @@ def test_max_k_limit_is_reported(cuda):
     assert st.max_k() >= 4096
     with pytest.raises(ValueError, match="exceeds the supported maximum"):
         st.search(np.zeros((1, 32), np.uint8), np.array([8], np.uint8), st.max_k() + 1)
+    st.close()
+
+
+def test_bulk_remove_resolves_move_chains(cuda):
+    """One remove call of half the store (tail rows included, so moved rows are removed again later in the batch): the
+    net parallel row moves must leave exactly the surviving rows, each with its own code and key."""
+    n = 300_000
+    keys, codes, lens = make_store_arrays(n, 77)
+    st = Store(key_bytes=8, max_bytes=32)
+    st.add(keys, codes, lens)
+    rng = np.random.default_rng(5)
+    gone = rng.permutation(n)[: n // 2]
+    gone = np.concatenate([gone, np.arange(n - 5000, n)])          # plus the whole tail: long chains
+    gone = np.unique(gone)
+    rng.shuffle(gone)
+    removed, cnt = st.remove(np.ascontiguousarray(keys[gone]), len(gone))
+    assert cnt == len(gone) and removed.all() and st.size() == n - len(gone)
+    keep = np.ones(n, dtype=bool)
+    keep[gone] = False
+    got_codes, got_lens = st.get(np.ascontiguousarray(keys[keep]), int(keep.sum()))
+    assert np.array_equal(got_lens, lens[keep]) and np.array_equal(got_codes, codes[keep])
+    assert not st.contains(np.ascontiguousarray(keys[gone][:1000]), 1000).any()
+    queries, qlens = synth.make_queries(32, n, 78, 77)
+    gk, gh, gn, gc, _ = st.search(queries, qlens, 50)
+    rows, h, nb, cnt2 = oracle_topk(keys[keep], codes[keep], lens[keep], queries, qlens, 50)
+    assert_same_topk(gk, gh, gn, gc, keys[keep], rows, h, nb, cnt2)
+    # and the store keeps working: re-add a part of what was removed
+    back = gone[:10_000]
+    assert st.add(np.ascontiguousarray(keys[back]), np.ascontiguousarray(codes[back]), np.ascontiguousarray(lens[back])).all()
+    keep[back] = True
+    gk, gh, gn, gc, _ = st.search(queries, qlens, 50)
+    rows, h, nb, cnt2 = oracle_topk(keys[keep], codes[keep], lens[keep], queries, qlens, 50)
+    assert_same_topk(gk, gh, gn, gc, keys[keep], rows, h, nb, cnt2)
     st.close()

@@ -83,6 +83,8 @@ def test_approximate_scoring_matches_reference():
             for j, (k, h, _n) in enumerate(hits):
                 keys[i, j], ham[i, j], vec[i, j] = np.frombuffer(k, np.uint8), h, np.frombuffer(st.get(k), np.uint8)
         doc_freq = case["doc_freq"]
+        from tests.fakes import OracleStore
+
         got = sp.score_approx(query, keys, ham, vec, counts, ndim, case["limit"], case["threshold"], True,
-                              lambda s: doc_freq.get(bytes(s).hex(), 0), case["total_assets"])
+                              lambda s: doc_freq.get(bytes(s).hex(), 0), case["total_assets"], scorer=OracleStore().score_segments)
         _check_results(got, case["result"])
