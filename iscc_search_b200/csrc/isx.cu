@@ -175,6 +175,7 @@ struct isx_store {
     PinnedBuf h_small_info;         // [8][4] status words written by the kernel
     PinnedBuf h_small_dbg;
     bool small_ok = true;           // cooperative launch available
+    int small_smem_max = -1;        // dynamic shared memory k_scan_small may use on this device (set on first use)
     // isx_search (host results): the fused select writes straight into the pinned result block (no D2H copies)
     uint64_t* small_host_khi = nullptr; uint64_t* small_host_klo = nullptr; uint16_t* small_host_h = nullptr;
     uint16_t* small_host_n = nullptr; uint32_t* small_host_cnt = nullptr;
@@ -397,7 +398,8 @@ static int launch_scan(isx_store* s, ScanParams& p, uint32_t we, uint32_t bpi_hi
     // whose CTAs all take equally long (measured on a 12.5 M-row shard, 8192 queries: 2 waves 81.7 ms, 4 waves 80.4, 8 waves 78.4)
     {
         uint32_t n_items = (p.block_end - p.block_begin + G - 1) / G;
-        uint32_t want = (uint32_t)s->sm_count * per_sm * 8;
+        static const uint32_t env_waves = [] { const char* e = getenv("ISX_SPLIT_WAVES"); return e ? (uint32_t)std::max(1, atoi(e)) : 8u; }();
+        uint32_t want = (uint32_t)s->sm_count * per_sm * env_waves;
         uint32_t splits = n_items >= want ? 1 : std::min<uint32_t>(p.T, (want + n_items - 1) / n_items);
         splits = std::min<uint32_t>(splits, std::max<uint32_t>(1, p.T / 32));  // >= 32 queries per CTA: its set-up (tables, tile) must stay small next to its work
         p.q_split = (p.T + splits - 1) / splits;
@@ -574,13 +576,14 @@ static int search_small(isx_store* s, const uint8_t* queries, bool q_on_device, 
     }
     const void* kern = env_wide ? (const void*)k_scan_small<3, 16> : (const void*)k_scan_small<5, 8>;
     const size_t smem = (env_wide ? sizeof(SmallSharedT<3, 16>) : sizeof(SmallSharedT<5, 8>)) + (size_t)Q * R * 4;
-    static int smem_max = -1;
-    if (smem_max < 0) {
+    // function attributes are per device: remembered per store (one store = one device), not in a process-wide static
+    if (s->small_smem_max < 0) {
         cudaFuncAttributes fa;
         CU(cudaFuncGetAttributes(&fa, kern));
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem_optin - (int)fa.sharedSizeBytes));
-        smem_max = s->max_smem_optin - (int)fa.sharedSizeBytes;
+        s->small_smem_max = s->max_smem_optin - (int)fa.sharedSizeBytes;
     }
+    const int smem_max = s->small_smem_max;
     if (smem > (size_t)smem_max) return 0;
     if (s->profiling) CU(cudaEventRecord(s->ev[0], s->stream));
     void* args[] = {&p};

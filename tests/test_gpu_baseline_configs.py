@@ -108,3 +108,33 @@ def test_concurrent_searches_and_mutations_are_serialised_safely(cuda):
     assert not errors, errors
     assert idx.size == n
     idx.close()
+
+
+def test_config3_batch_shape_every_query_bit_exact(cuda):
+    """
+    Config 3's launch plan at reduced row count: 10 000 mixed-length queries = two tiles (2048 + ~450) per query length on
+    alternating tile lanes, warm-up ranges, forked scan streams - EVERY query against the oracle (the tuned CPU arm, itself
+    checked against the plain restatement in tests/test_oracle.py), through the device-resident batch entry point.
+    """
+    import torch
+
+    from iscc_search_b200.sharded import ShardedSearcher
+    from oracle import c_oracle
+
+    n, q, k, seed = 3_000_000, 10_000, 100, 303
+    dev = torch.device("cuda", 0)
+    st = Store(key_bytes=8, max_bytes=32)
+    st.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    d_keys = torch.empty(n * 8, dtype=torch.uint8, device=dev)
+    d_codes = torch.empty(n * 32, dtype=torch.uint8, device=dev)
+    d_lens = torch.empty(n, dtype=torch.uint8, device=dev)
+    st.synth_rows_device(seed, 0, n, d_keys.data_ptr(), d_codes.data_ptr(), d_lens.data_ptr())
+    st.add_device(d_keys.data_ptr(), d_codes.data_ptr(), d_lens.data_ptr(), n)
+    queries, qlens = synth.make_queries(q, n, seed + 1, seed)
+    gk, gh, gn, gc = (a.copy() for a in ShardedSearcher(st, 0, 1, None, dev).search(queries, qlens, k))
+    assert st.stats()["passes"] == 8   # 4 query lengths x 2 tiles
+    khi, _, codes, lens = c_oracle.synth_rows(0, n, seed)
+    rows, h, nb, cnt = c_oracle.SoaStore(khi, None, codes, lens).topk(queries, qlens, k)
+    assert_same_topk(gk, gh, gn, gc, khi, rows, h, nb, cnt)
+    st.set_stream(None)
+    st.close()
