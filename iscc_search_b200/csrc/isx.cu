@@ -293,7 +293,8 @@ static int sync_map(isx_store* s) {
         for (uint32_t r = m0; r < n; r++) {
             const Key128 key{sg.h_khi[r], s->key_bytes == 16 ? sg.h_klo[r] : 0};
             if (!s->map.insert(key, ((uint64_t)sid << 32) | r))
-                return fail(ISX_EINVAL, "isx_add_device: bulk-appended keys were not unique (key %016llx%016llx is stored twice)",
+                return fail(ISX_EINVAL, "isx_add_device: bulk-appended keys were not unique (key %016llx%016llx is stored twice); the key map "
+                                        "cannot be completed - clear or reload the store (searches still work)",
                             (unsigned long long)key.hi, (unsigned long long)key.lo);
         }
         sg.mirrored = n;
