@@ -403,6 +403,7 @@ static int launch_scan(isx_store* s, ScanParams& p, uint32_t we, uint32_t bpi_hi
         uint32_t want = (uint32_t)s->sm_count * per_sm * env_waves;
         uint32_t splits = n_items >= want ? 1 : std::min<uint32_t>(p.T, (want + n_items - 1) / n_items);
         splits = std::min<uint32_t>(splits, std::max<uint32_t>(1, p.T / 32));  // >= 32 queries per CTA: its set-up (tables, tile) must stay small next to its work
+        splits = std::max<uint32_t>(splits, (p.T + kMaxTile - 1) / kMaxTile);   // a CTA holds at most kMaxTile queries in shared memory
         p.q_split = (p.T + splits - 1) / splits;
     }
     switch (we) {
@@ -701,7 +702,11 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
     // tile size from a scratch budget
     const size_t per_query = (size_t)C * 8 + (size_t)R * 4 + 64;
     const size_t budget = (size_t)6 << 30;
-    uint32_t tile_max = (uint32_t)std::max<size_t>(1, std::min<size_t>(kMaxTile, budget / per_query));
+    // queries per tile (one pass over the store): up to 2 x kMaxTile - a launch then splits the tile over gridDim.y so that a
+    // CTA keeps at most kMaxTile queries in shared memory; fewer, larger tiles halve the per-tile fixed work (bootstrap
+    // sample, warm-up ranges, select) of a 10 000-query batch
+    static const size_t env_tile = [] { const char* e = getenv("ISX_MAX_TILE"); return e ? (size_t)std::max(64, atoi(e)) : (size_t)kMaxTile; }();
+    uint32_t tile_max = (uint32_t)std::max<size_t>(1, std::min<size_t>(env_tile, budget / per_query));
     tile_max = std::min<uint32_t>(tile_max, (uint32_t)Q);
 
     uint32_t big_P = 0;
@@ -763,7 +768,12 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
         const uint32_t Lq = qlens[order[g0]];
         size_t g1 = g0;
         while (g1 < Q && qlens[order[g1]] == Lq) g1++;
-        for (size_t t0 = g0; t0 < g1; t0 += tile_max) tiles.push_back(Tile{t0, (uint32_t)std::min<size_t>(tile_max, g1 - t0), Lq});
+        {   // equal tiles per query length (2500 queries -> 2 x 1250, not 2048 + 452: the small tail tile ran at low efficiency)
+            static const bool env_balance = [] { const char* e = getenv("ISX_TILE_BALANCE"); return !(e && e[0] == '0'); }();
+            const size_t n = g1 - g0, n_tiles = (n + tile_max - 1) / tile_max;
+            const size_t step = env_balance ? (n + n_tiles - 1) / n_tiles : tile_max;
+            for (size_t t0 = g0; t0 < g1; t0 += step) tiles.push_back(Tile{t0, (uint32_t)std::min<size_t>(step, g1 - t0), Lq});
+        }
         g0 = g1;
     }
     if (s->h_flags.ensure(Q * 16)) return ISX_ENOMEM;
@@ -851,7 +861,10 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
         if (n_blocks_total > 0) {
             // batches: 64 blocks, refined by the two warm-up ranges below; small tiles: ~1 % of the store, because
             // their threshold feedback is slow relative to the scan (the first items of all CTAs run at once)
-            uint32_t want = T >= 64 ? 64 : std::min<uint32_t>(1024, std::max<uint32_t>(64, n_blocks_total / 128));
+            // (with shared thresholds every rank samples 1/world of that: the warm-up ranges refine the bound from the
+            //  GLOBAL histograms right after, and the sample is pure per-tile overhead on a small shard)
+            uint32_t want = T >= 64 ? (share_on ? std::max(8u, 64u / s->share_world) : 64u)
+                                    : std::min<uint32_t>(1024, std::max<uint32_t>(64, n_blocks_total / 128));
             want = std::max<uint32_t>(want, (4 * k + kBlockRows - 1) / kBlockRows);
             SampleParams sp{};
             uint32_t total = 0;
