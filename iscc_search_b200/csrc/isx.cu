@@ -861,10 +861,9 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
         if (n_blocks_total > 0) {
             // batches: 64 blocks, refined by the two warm-up ranges below; small tiles: ~1 % of the store, because
             // their threshold feedback is slow relative to the scan (the first items of all CTAs run at once)
-            // (with shared thresholds every rank samples 1/world of that: the warm-up ranges refine the bound from the
-            //  GLOBAL histograms right after, and the sample is pure per-tile overhead on a small shard)
-            uint32_t want = T >= 64 ? (share_on ? std::max(8u, 64u / s->share_world) : 64u)
-                                    : std::min<uint32_t>(1024, std::max<uint32_t>(64, n_blocks_total / 128));
+            // (sampling only 64 / world blocks per rank under shared thresholds was tried on 8 GPUs: 66.7 vs 65.2 ms per step,
+            //  the looser first bounds cost more than the smaller sample saves - profiles/r02i_cfg3_n8.json)
+            uint32_t want = T >= 64 ? 64 : std::min<uint32_t>(1024, std::max<uint32_t>(64, n_blocks_total / 128));
             want = std::max<uint32_t>(want, (4 * k + kBlockRows - 1) / kBlockRows);
             SampleParams sp{};
             uint32_t total = 0;
