@@ -122,6 +122,11 @@ int isx_contains(isx_store_t* s, const void* keys, size_t n, uint8_t* present);
 int isx_get(isx_store_t* s, const void* keys, size_t n, uint8_t* codes_out, uint8_t* lens_out);
 int isx_size(isx_store_t* s, uint64_t* n_out);
 int isx_clear(isx_store_t* s);
+/* Free the per-search working memory of a store (candidate lists, histograms, result / staging buffers: up to a few GB
+ * after a large batch); it re-grows on demand. Rows and keys are untouched. A process that keeps many stores open
+ * (one per unit type and simprint type of every index, iscc_search/indexes/usearch/manager.py:258-279) calls this after
+ * batch work so that idle stores do not pin HBM next to the data. */
+int isx_release_scratch(isx_store_t* s, uint64_t* bytes_freed);
 /* bytes of device memory currently allocated for rows (planes + keys) */
 int isx_device_bytes(isx_store_t* s, uint64_t* n_out);
 /* bit L-1 set when at least one stored code has L bytes */

@@ -49,7 +49,7 @@ _lib = None
 SYMBOLS = (
     "isx_last_error", "isx_abi_version", "isx_device_count", "isx_open", "isx_close", "isx_set_stream",
     "isx_set_profiling", "isx_get_stats", "isx_add", "isx_add_device", "isx_synth_rows_device", "isx_remove", "isx_contains", "isx_get", "isx_size",
-    "isx_clear", "isx_device_bytes", "isx_length_mask", "isx_save", "isx_load", "isx_search",
+    "isx_clear", "isx_release_scratch", "isx_device_bytes", "isx_length_mask", "isx_save", "isx_load", "isx_search",
     "isx_search_device", "isx_merge_device", "isx_max_k", "isx_match_all", "isx_score_segments", "isx_share_init", "isx_share_attach",
     "isx_share_reset", "isx_share_set_lengths", "isx_selftest_rank_table", "isx_selftest_keymap", "isx_selftest_distance",
 )
@@ -99,6 +99,7 @@ def lib():
     L.isx_size.argtypes = [vp, P(u64)]
     L.isx_clear.argtypes = [vp]
     L.isx_device_bytes.argtypes = [vp, P(u64)]
+    L.isx_release_scratch.argtypes = [vp, P(u64)]
     L.isx_length_mask.argtypes = [vp, P(u32)]
     L.isx_save.argtypes = [vp, cp]
     L.isx_load.argtypes = [vp, cp]
@@ -196,6 +197,13 @@ class Store:
 
     def clear(self):
         check(lib().isx_clear(self.handle))
+
+    def release_scratch(self):
+        # type: () -> int
+        """Free the per-search working memory (re-grows on demand); returns the bytes freed."""
+        n = ctypes.c_uint64()
+        check(lib().isx_release_scratch(self.handle, ctypes.byref(n)))
+        return int(n.value)
 
     def add(self, keys, codes, lens):
         # type: (np.ndarray, np.ndarray, np.ndarray) -> np.ndarray

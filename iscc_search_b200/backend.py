@@ -417,9 +417,22 @@ class B200Index:
     def search_assets(self, query, limit=100, exact=False):
         return self.search_assets_batch([query], limit, exact)[0]
 
+    def release_scratch(self):
+        # type: () -> int
+        """Free the per-search working memory of every derived store of this index (rows stay); returns the bytes freed."""
+        stores = list(self._nphd_indexes.values()) + list(self._simprint_indexes.values()) + [self._instance]
+        return sum(store.release_scratch() for store in stores)
+
     def search_assets_batch(self, queries, limit=100, exact=False):
         # type: (list, int, bool) -> list
         """Many queries at once: one GPU batch per unit type; each result equals `search_assets(query)`."""
+        try:
+            return self._search_assets_batch(queries, limit, exact)
+        finally:
+            if len(queries) >= 1024:   # a large batch grows GB of candidate lists per store: give them back
+                self.release_scratch()
+
+    def _search_assets_batch(self, queries, limit=100, exact=False):
         schema = entries.schema
         prepared = []
         for query in queries:
@@ -708,6 +721,13 @@ class B200IndexManager:
     def search_assets_batch(self, index_name, queries, limit=100):
         self._validate_index_exists(index_name)
         return self._get_or_load_index(index_name).search_assets_batch(queries, limit)
+
+    def release_scratch(self, index_name=None):
+        # type: (str | None) -> int
+        """Free the GPU working memory of one index, or of every index this manager has open (extension; rows stay resident)."""
+        with self._lock:
+            indexes = [self._get_or_load_index(index_name)] if index_name is not None else list(self._index_cache.values())
+        return sum(idx.release_scratch() for idx in indexes)
 
     def rebuild(self, name, unit_types=None, simprint_types=None):
         self._validate_index_exists(name)

@@ -1104,6 +1104,24 @@ int isx_close(isx_store_t* s) {
     return 0;
 }
 
+int isx_release_scratch(isx_store_t* s, uint64_t* bytes_freed) {
+    if (!s) return fail(ISX_EINVAL, "store is NULL");
+    std::shared_lock<std::shared_mutex> g(s->rows_mu);
+    std::lock_guard<std::mutex> gw(s->work_mu);
+    int rc = set_device(s);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    // per-search working memory only (candidate lists, histograms, result and staging buffers): everything re-grows on
+    // demand; rows, keys, descriptors, rank tables and the small-batch state stay
+    DevBuf* bufs[] = {&s->d_stage_codes, &s->d_stage_keys, &s->d_stage_dest, &s->d_moves, &s->d_queries, &s->d_tau, &s->d_hist, &s->d_shist,
+                      &s->d_cnt, &s->d_ovf, &s->d_cand, &s->d_qmap, &s->d_fb, &s->d_fb_cand, &s->d_out_khi, &s->d_out_klo, &s->d_out_h,
+                      &s->d_out_n, &s->d_out_cnt, &s->d_out_codes, &s->d_bigsort, &s->d_bulk};
+    uint64_t freed = 0;
+    for (DevBuf* b : bufs) { freed += b->cap; b->release(); }
+    if (bytes_freed) *bytes_freed = freed;
+    return 0;
+}
+
 int isx_set_stream(isx_store_t* s, void* cuda_stream) {
     if (!s) return fail(ISX_EINVAL, "store is NULL");
     std::lock_guard<std::mutex> g(s->work_mu);

@@ -160,5 +160,8 @@ class InstancePrefixIndex:
     def __len__(self):
         return self._store.size()
 
+    def release_scratch(self):
+        return self._store.release_scratch()
+
     def close(self):
         self._store.close()

@@ -148,6 +148,10 @@ class _IndexBase:
     def stats(self):
         return self._store.stats()
 
+    def release_scratch(self):
+        """Free the store's per-search working memory (include/isx.h: isx_release_scratch); returns the bytes freed."""
+        return self._store.release_scratch()
+
 
 class ShardedNphdIndex(_IndexBase):
     """
@@ -343,7 +347,13 @@ class ShardedIndex128(_IndexBase):
                             visited_members=n_rows * len(qlens), computed_distances=n_rows * len(qlens))
 
 
-class MultiDeviceNphdIndex:
+class _MultiScratch:
+    def release_scratch(self):
+        """Free the per-search working memory of every device's store."""
+        return sum(shard.release_scratch() for shard in self.shards)
+
+
+class MultiDeviceNphdIndex(_MultiScratch):
     """
     `ShardedNphdIndex` row-sharded over several GPUs of ONE process.
 
@@ -486,7 +496,7 @@ class MultiDeviceNphdIndex:
         return [s.stats() for s in self.shards]
 
 
-class MultiDeviceIndex128:
+class MultiDeviceIndex128(_MultiScratch):
     """
     `ShardedIndex128` row-sharded over several GPUs of ONE process (see `MultiDeviceNphdIndex`).
 

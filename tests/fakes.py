@@ -18,6 +18,9 @@ class OracleStore:
         self.rows = {}  # key (int | bytes16) -> code bytes, insertion ordered
         self.launches = 0
 
+    def release_scratch(self):
+        return 0
+
     def score_segments(self, seg, rec_qi, rec_sim, rec_idf, q_idf):
         """Test double of isx_score_segments: the same sums as plain Python floats (left to right, no compensation)."""
         out = np.zeros(len(seg) - 1, dtype=np.float64)

@@ -258,3 +258,22 @@ def test_bulk_remove_resolves_move_chains(cuda):
     rows, h, nb, cnt2 = oracle_topk(keys[keep], codes[keep], lens[keep], queries, qlens, 50)
     assert_same_topk(gk, gh, gn, gc, keys[keep], rows, h, nb, cnt2)
     st.close()
+
+
+def test_release_scratch_frees_working_memory_and_searches_keep_working(cuda):
+    n = 200_000
+    keys, codes, lens = make_store_arrays(n, 91)
+    st = Store(key_bytes=8, max_bytes=32)
+    st.add(keys, codes, lens)
+    queries, qlens = synth.make_queries(3000, n, 92, 91)
+    first = st.search(queries, qlens, 100)
+    freed = st.release_scratch()
+    assert freed > 100 * 2**20          # candidate lists of a 3000-query batch
+    assert st.release_scratch() == 0
+    again = st.search(queries, qlens, 100)
+    for a, b in zip(first[:4], again[:4]):
+        assert np.array_equal(a, b)
+    one = st.search(queries[:1], qlens[:1], 10)        # small-batch path after a release
+    rows, h, nb, cnt = oracle_topk(keys, codes, lens, queries[:1], qlens[:1], 10)
+    assert_same_topk(one[0], one[1], one[2], one[3], keys, rows, h, nb, cnt)
+    st.close()
