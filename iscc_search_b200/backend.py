@@ -725,8 +725,12 @@ class B200IndexManager:
     def release_scratch(self, index_name=None):
         # type: (str | None) -> int
         """Free the GPU working memory of one index, or of every index this manager has open (extension; rows stay resident)."""
-        with self._lock:
-            indexes = [self._get_or_load_index(index_name)] if index_name is not None else list(self._index_cache.values())
+        if index_name is not None:
+            self._validate_index_exists(index_name)
+            indexes = [self._get_or_load_index(index_name)]
+        else:
+            with self._cache_lock:
+                indexes = list(self._index_cache.values())
         return sum(idx.release_scratch() for idx in indexes)
 
     def rebuild(self, name, unit_types=None, simprint_types=None):

@@ -29,3 +29,17 @@ def test_multi_device_equals_single(tmp_path, cpu_stores):
 
 def test_crash_recovery(tmp_path, cpu_stores):
     protocol_cases.case_crash_recovery(tmp_path)
+
+
+def test_manager_release_scratch_is_callable_on_open_indexes(cpu_stores, tmp_path):
+    from iscc_search_b200 import B200IndexManager
+    from iscc_search_b200.schema import IsccIndex
+
+    m = B200IndexManager(tmp_path)
+    m.create_index(IsccIndex(name="a"))
+    assert m.release_scratch() == 0 and m.release_scratch("a") == 0
+    import pytest
+
+    with pytest.raises(FileNotFoundError):
+        m.release_scratch("nope")
+    m.close()
