@@ -42,9 +42,46 @@ DEFAULT_OPTIONS = {
     # extension: > 0 routes the unit searches of concurrent `search_assets` calls (the REST server's thread pool,
     # server/search.py) through one `BatchingFrontDoor` per unit type, so they share GPU batches; 0 = one search per unit
     "coalesce_ms": 0.0,
+    # host store of assets / metadata: "log" = assetlog.AssetLog (append log, no dependency), "lmdb" = lmdblog.LmdbAssetLog (the
+    # reference's own index.lmdb tables, needs the `lmdb` package), "auto" = whatever the directory already holds, else
+    # LMDB when the package is importable, else the log
+    "asset_store": "auto",
 }
 
 SP_FINGERPRINT_BYTES = 16
+ASSET_STORE_MARKERS = ("index.meta.json", "index.lmdb")   # AssetLog.META, LmdbAssetLog.META
+
+
+def _lmdb_module():
+    try:
+        import lmdb
+
+        return lmdb
+    except ImportError:
+        return None
+
+
+def open_asset_store(path, kind="auto", realm_id=None, max_dim=256):
+    # type: (str | Path, str, int | None, int) -> object
+    """The host store of an index directory behind the `AssetLog` interface (see DEFAULT_OPTIONS["asset_store"])."""
+    from iscc_search_b200.lmdblog import LmdbAssetLog
+
+    path = Path(path)
+    if kind not in ("auto", "log", "lmdb"):
+        raise ValueError(f"asset_store must be 'auto', 'log' or 'lmdb', got {kind!r}")
+    if kind == "auto":
+        if (path / AssetLog.META).exists():
+            kind = "log"
+        elif (path / LmdbAssetLog.META).exists():
+            kind = "lmdb"
+        else:
+            kind = "lmdb" if _lmdb_module() is not None else "log"
+    if kind == "lmdb":
+        module = _lmdb_module()
+        if module is None:
+            raise ImportError(f"'{path}' needs the `lmdb` package (asset_store='lmdb' / an existing index.lmdb)")
+        return LmdbAssetLog(path, realm_id=realm_id, max_dim=max_dim, lmdb_module=module)
+    return AssetLog(path, realm_id=realm_id, max_dim=max_dim)
 
 
 def set_schema(module):
@@ -103,7 +140,7 @@ class B200Index:
         self._opts = dict(DEFAULT_OPTIONS, **options)
         self.path = Path(path)
         self._stores = stores if stores is not None else GpuStores(device)
-        self._log = AssetLog(self.path, realm_id=realm_id, max_dim=max_dim)
+        self._log = open_asset_store(self.path, self._opts["asset_store"], realm_id=realm_id, max_dim=max_dim)
         self.max_dim = self._log.max_dim
         self._realm_id = self._log.realm_id
         self._nphd_indexes = {}      # unit_type -> ShardedNphdIndex
@@ -656,7 +693,7 @@ def _as_query_simprints(simprints):
 class B200IndexManager:
     """IsccIndexProtocol over a directory of `B200Index` sub-directories. Mirrors `UsearchIndexManager`."""
 
-    MARKER = AssetLog.META
+    MARKER = AssetLog.META   # (either of ASSET_STORE_MARKERS marks an index directory)
 
     def __init__(self, base_path, max_dim=256, device=0, stores=None, **options):
         self.base_path = Path(base_path)
@@ -670,7 +707,7 @@ class B200IndexManager:
         schema = entries.schema
         found = []
         for index_dir in self.base_path.iterdir():
-            if not index_dir.is_dir() or not (index_dir / self.MARKER).exists():
+            if not index_dir.is_dir() or not any((index_dir / m).exists() for m in ASSET_STORE_MARKERS):
                 continue
             try:
                 idx = self._get_or_load_index(index_dir.name)
@@ -763,7 +800,7 @@ class B200IndexManager:
             return self._index_cache[name]
 
     def _validate_index_exists(self, name):
-        if not (self.base_path / name / self.MARKER).exists():
+        if not any((self.base_path / name / m).exists() for m in ASSET_STORE_MARKERS):
             raise FileNotFoundError(f"Index '{name}' not found")
 
     @staticmethod
