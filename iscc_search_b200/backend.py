@@ -52,13 +52,13 @@ SP_FINGERPRINT_BYTES = 16
 ASSET_STORE_MARKERS = ("index.meta.json", "index.lmdb")   # AssetLog.META, LmdbAssetLog.META
 
 
-def _lmdb_module():
+def _lmdb_module(real_only=False):
+    """The `lmdb` package, or None. `real_only`: ignore stand-ins without py-lmdb's `Environment` class (test doubles)."""
     try:
         import lmdb
-
-        return lmdb
     except ImportError:
         return None
+    return lmdb if (not real_only or hasattr(lmdb, "Environment")) else None
 
 
 def open_asset_store(path, kind="auto", realm_id=None, max_dim=256):
@@ -75,7 +75,7 @@ def open_asset_store(path, kind="auto", realm_id=None, max_dim=256):
         elif (path / LmdbAssetLog.META).exists():
             kind = "lmdb"
         else:
-            kind = "lmdb" if _lmdb_module() is not None else "log"
+            kind = "lmdb" if _lmdb_module(real_only=True) is not None else "log"
     if kind == "lmdb":
         module = _lmdb_module()
         if module is None:
