@@ -53,12 +53,12 @@ ASSET_STORE_MARKERS = ("index.meta.json", "index.lmdb")   # AssetLog.META, LmdbA
 
 
 def _lmdb_module(real_only=False):
-    """The `lmdb` package, or None. `real_only`: ignore stand-ins without py-lmdb's `Environment` class (test doubles)."""
+    """The `lmdb` package, or None. `real_only`: ignore stand-ins that do not report a py-lmdb version (test doubles)."""
     try:
         import lmdb
     except ImportError:
         return None
-    return lmdb if (not real_only or hasattr(lmdb, "Environment")) else None
+    return lmdb if (not real_only or hasattr(lmdb, "__version__")) else None
 
 
 def open_asset_store(path, kind="auto", realm_id=None, max_dim=256):
