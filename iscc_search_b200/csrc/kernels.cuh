@@ -17,6 +17,9 @@
 // candidates; the final kernel cuts at the exact k-th rank and breaks ties by key.
 #pragma once
 #include <cstdint>
+#ifndef ISX_PAIR_VOTE
+#define ISX_PAIR_VOTE 0
+#endif
 #include <cuda_runtime.h>
 
 namespace isx {
@@ -357,14 +360,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_scan(const __grid_constant__
                 }
                 const uint32_t hmax = hv & 0xfffu;
                 const uint32_t tier = hv >> 12;   // filter tier, uniform per query
-#pragma unroll
-                for (int g = 0; g < G; g++) {
-                    if (tier) {
-                        const uint32_t lbmin = (LowerBound<WE>::kCutoff3 && tier == 3)
-                                                   ? LowerBound<WE>::template min4<3>(a[g], qv, mask_last)
-                                                   : LowerBound<WE>::template min4<2>(a[g], qv, mask_last);
-                        if (!__any_sync(0xffffffffu, lbmin <= hmax)) continue;  // no lane can have a candidate in this slot
-                    }
+                auto exact_and_emit = [&](int g) {
                     uint32_t d[4];
 #pragma unroll
                     for (int r = 0; r < 4; r++) {
@@ -376,6 +372,29 @@ __global__ void __launch_bounds__(kThreads, MINB) k_scan(const __grid_constant__
                     const uint32_t dmin = min(min(d[0], d[1]), min(d[2], d[3]));
                     if (__any_sync(0xffffffffu, dmin <= hmax))
                         emit_group(p, q0 + q, hmax, d[0], d[1], d[2], d[3], seg_id[g], row0[g], seg_n[g], s_rank, nullptr);
+                };
+                auto bound_of = [&](int g) -> uint32_t {
+                    return (LowerBound<WE>::kCutoff3 && tier == 3) ? LowerBound<WE>::template min4<3>(a[g], qv, mask_last)
+                                                                   : LowerBound<WE>::template min4<2>(a[g], qv, mask_last);
+                };
+#if ISX_PAIR_VOTE
+                if (tier && G >= 2) {   // A/B variant: one vote per PAIR of 4-row groups, per-group votes only when the pair passes
+#pragma unroll
+                    for (int g = 0; g + 1 < G; g += 2) {
+                        const uint32_t lb0 = bound_of(g), lb1 = bound_of(g + 1);
+                        if (!__any_sync(0xffffffffu, min(lb0, lb1) <= hmax)) continue;
+                        if (__any_sync(0xffffffffu, lb0 <= hmax)) exact_and_emit(g);
+                        if (__any_sync(0xffffffffu, lb1 <= hmax)) exact_and_emit(g + 1);
+                    }
+                    continue;
+                }
+#endif
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    if (tier) {
+                        if (!__any_sync(0xffffffffu, bound_of(g) <= hmax)) continue;  // no lane can have a candidate in this slot
+                    }
+                    exact_and_emit(g);
                 }
             }
         }
