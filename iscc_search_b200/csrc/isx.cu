@@ -875,8 +875,12 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
                 total += take;
             }
             sp.prefix[kMaxBytes + 1] = total;
-            size_t smem = (size_t)R * 4 + 258 * 2 + 16;
-            k_sample<<<dim3(total, T, 1), kThreads, smem, ts>>>(p, sp, d_shist);
+            // queries per sample CTA: their histograms share 32 KB of shared memory (21 queries at R = 385)
+            sp.q_per_cta = std::max<uint32_t>(1, std::min<uint32_t>(T, (32u * 1024) / (R * 4)));
+            sp.tail_only = (uint64_t)4 * k * 16 <= (uint64_t)total * kBlockRows ? 1 : 0;
+            size_t smem = (size_t)sp.q_per_cta * R * 4 + 258 * 2 + 16;
+            if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_sample<<<dim3(total, (T + sp.q_per_cta - 1) / sp.q_per_cta, 1), kThreads, smem, ts>>>(p, sp, d_shist);
             CU(cudaGetLastError());
             k_sample_tau<<<(T * 32 + 255) / 256, 256, 0, ts>>>(d_shist, p.tau, T, R, k);
             CU(cudaGetLastError());

@@ -413,56 +413,70 @@ __global__ void __launch_bounds__(kThreads, MINB) k_scan(const __grid_constant__
 struct SampleParams {
     uint32_t bucket_first_block[kMaxBytes + 1];  // [L] first block of bucket L in the block list
     uint32_t prefix[kMaxBytes + 2];              // [L] sample blocks taken from buckets < L; [33] = total
+    uint32_t q_per_cta;                          // queries one CTA histograms for its block (shared-memory bound)
+    uint32_t tail_only;                          // 1: only rows in the lower tail (h <= mean - 1.5 sigma of a random pair) are
+                                                 // counted - the k-th rank of the sample lies there whenever 4k <= rows / 16
 };
 
+// One CTA = one sampled block of 1024 rows x a sub-tile of queries: the rows are loaded once (4 per thread) and scored
+// against every query of the sub-tile, each query with its own shared-memory histogram (round 1 launched one CTA per
+// (block, query): 82 000 CTAs of a microsecond each for a 1250-query tile).
 template <int WE>
-__device__ __forceinline__ void sample_body(const ScanParams& p, const SegDesc& sd, uint32_t blk_row, uint32_t m, uint32_t q,
-                                            uint32_t* s_hist, const uint16_t* s_rank) {
+__device__ __forceinline__ void sample_body(const ScanParams& p, const SampleParams& sp, const SegDesc& sd, uint32_t blk_row, uint32_t m,
+                                            uint32_t q0, uint32_t nq, uint32_t* s_hist, const uint16_t* s_rank) {
     const uint32_t tid = threadIdx.x;
     const uint32_t mask_last = (m & 3u) ? ((1u << (8u * (m & 3u))) - 1u) : 0xffffffffu;
     const uint32_t row0 = blk_row + tid * 4;
-    uint32_t x0[WE], x1[WE], x2[WE], x3[WE];
+    uint4 a[WE];
 #pragma unroll
-    for (int w = 0; w < WE; w++) {
-        const uint4 a = ldg_stream(sd.planes + (size_t)w * sd.cap + row0);
-        const uint32_t qv = p.queries[(size_t)q * 8 + w];
-        const uint32_t mk = (w == WE - 1) ? mask_last : 0xffffffffu;
-        x0[w] = (a.x ^ qv) & mk; x1[w] = (a.y ^ qv) & mk; x2[w] = (a.z ^ qv) & mk; x3[w] = (a.w ^ qv) & mk;
+    for (int w = 0; w < WE; w++) a[w] = ldg_stream(sd.planes + (size_t)w * sd.cap + row0);
+    const float mean = 4.0f * (float)m, sigma = sqrtf(2.0f * (float)m);
+    const uint32_t hcut = sp.tail_only ? (uint32_t)fmaxf(0.0f, mean - 1.5f * sigma) : 8u * m;
+    for (uint32_t qi = 0; qi < nq; qi++) {
+        const uint32_t* qsrc = p.queries + (size_t)(q0 + qi) * 8;
+        uint32_t x0[WE], x1[WE], x2[WE], x3[WE];
+#pragma unroll
+        for (int w = 0; w < WE; w++) {
+            const uint32_t qv = __ldg(&qsrc[w]);
+            const uint32_t mk = (w == WE - 1) ? mask_last : 0xffffffffu;
+            x0[w] = (a[w].x ^ qv) & mk; x1[w] = (a[w].y ^ qv) & mk; x2[w] = (a[w].z ^ qv) & mk; x3[w] = (a[w].w ^ qv) & mk;
+        }
+        const uint32_t d[4] = {pair_distance<WE>(x0), pair_distance<WE>(x1), pair_distance<WE>(x2), pair_distance<WE>(x3)};
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            if (d[r] <= hcut && row0 + r < sd.n) atomicAdd(&s_hist[qi * p.R + s_rank[d[r]]], 1u);
     }
-    const uint32_t d[4] = {pair_distance<WE>(x0), pair_distance<WE>(x1), pair_distance<WE>(x2), pair_distance<WE>(x3)};
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-        if (row0 + r < sd.n) atomicAdd(&s_hist[s_rank[d[r]]], 1u);
 }
 
 __global__ void __launch_bounds__(kThreads) k_sample(const __grid_constant__ ScanParams p, const __grid_constant__ SampleParams sp,
                                                       uint32_t* __restrict__ sample_hist) {
     extern __shared__ uint4 smem_raw[];
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw);       // [R]
-    uint16_t* s_rank = reinterpret_cast<uint16_t*>(s_hist + p.R);   // [258]
-    const uint32_t tid = threadIdx.x, q = blockIdx.y;
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw);                       // [q_per_cta][R]
+    uint16_t* s_rank = reinterpret_cast<uint16_t*>(s_hist + (size_t)sp.q_per_cta * p.R);   // [258]
+    const uint32_t tid = threadIdx.x;
+    const uint32_t q0 = blockIdx.y * sp.q_per_cta, nq = min(sp.q_per_cta, p.T - q0);
     uint32_t L = 1;
     while (L < kMaxBytes && blockIdx.x >= sp.prefix[L + 1]) L++;    // bucket of this sample block (uniform)
     const uint2 blk = p.blocks[sp.bucket_first_block[L] + (blockIdx.x - sp.prefix[L])];
     const SegDesc sd = p.segs[blk.x];
     const uint32_t m = min(p.qlen_bytes, sd.len_bytes);
-    for (uint32_t i = tid; i < p.R; i += kThreads) s_hist[i] = 0;
+    for (uint32_t i = tid; i < nq * p.R; i += kThreads) s_hist[i] = 0;
     for (uint32_t i = tid; i < 257; i += kThreads) s_rank[i] = p.rank_tab[m * 257 + i];
     __syncthreads();
     switch ((m + 3) / 4) {
-        case 1: sample_body<1>(p, sd, blk.y, m, q, s_hist, s_rank); break;
-        case 2: sample_body<2>(p, sd, blk.y, m, q, s_hist, s_rank); break;
-        case 3: sample_body<3>(p, sd, blk.y, m, q, s_hist, s_rank); break;
-        case 4: sample_body<4>(p, sd, blk.y, m, q, s_hist, s_rank); break;
-        case 5: sample_body<5>(p, sd, blk.y, m, q, s_hist, s_rank); break;
-        case 6: sample_body<6>(p, sd, blk.y, m, q, s_hist, s_rank); break;
-        case 7: sample_body<7>(p, sd, blk.y, m, q, s_hist, s_rank); break;
-        default: sample_body<8>(p, sd, blk.y, m, q, s_hist, s_rank); break;
+        case 1: sample_body<1>(p, sp, sd, blk.y, m, q0, nq, s_hist, s_rank); break;
+        case 2: sample_body<2>(p, sp, sd, blk.y, m, q0, nq, s_hist, s_rank); break;
+        case 3: sample_body<3>(p, sp, sd, blk.y, m, q0, nq, s_hist, s_rank); break;
+        case 4: sample_body<4>(p, sp, sd, blk.y, m, q0, nq, s_hist, s_rank); break;
+        case 5: sample_body<5>(p, sp, sd, blk.y, m, q0, nq, s_hist, s_rank); break;
+        case 6: sample_body<6>(p, sp, sd, blk.y, m, q0, nq, s_hist, s_rank); break;
+        case 7: sample_body<7>(p, sp, sd, blk.y, m, q0, nq, s_hist, s_rank); break;
+        default: sample_body<8>(p, sp, sd, blk.y, m, q0, nq, s_hist, s_rank); break;
     }
     __syncthreads();
-    for (uint32_t i = tid; i < p.R; i += kThreads) {
+    for (uint32_t i = tid; i < nq * p.R; i += kThreads) {
         const uint32_t v = s_hist[i];
-        if (v) atomicAdd(&sample_hist[(size_t)q * p.R + i], v);
+        if (v) atomicAdd(&sample_hist[(size_t)q0 * p.R + i], v);
     }
 }
 
