@@ -863,7 +863,8 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
             // their threshold feedback is slow relative to the scan (the first items of all CTAs run at once)
             // (sampling only 64 / world blocks per rank under shared thresholds was tried on 8 GPUs: 66.7 vs 65.2 ms per step,
             //  the looser first bounds cost more than the smaller sample saves - profiles/r02i_cfg3_n8.json)
-            uint32_t want = T >= 64 ? 64 : std::min<uint32_t>(1024, std::max<uint32_t>(64, n_blocks_total / 128));
+            static const uint32_t env_sample = [] { const char* e = getenv("ISX_SAMPLE_BLOCKS"); return e ? (uint32_t)std::max(1, atoi(e)) : 64u; }();
+            uint32_t want = T >= 64 ? env_sample : std::min<uint32_t>(1024, std::max<uint32_t>(64, n_blocks_total / 128));
             want = std::max<uint32_t>(want, (4 * k + kBlockRows - 1) / kBlockRows);
             SampleParams sp{};
             uint32_t total = 0;
@@ -895,8 +896,10 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
             // with shared thresholds all ranks warm up at once on `world` times the rows: each rank's share of the two
             // ranges shrinks accordingly (the ranges run at low occupancy, 5 % of a 12.5 M-row shard otherwise)
             const uint32_t w = share_on ? s->share_world : 1;
+            static const int env_warm = [] { const char* e = getenv("ISX_WARM_RANGES"); return e ? atoi(e) : 2; }();
+            int wi = 0;
             for (uint32_t span : {std::max(8u, 64u / w), std::max(64u, 512u / w)}) {
-                if (n_blocks_total - done <= span * 4) break;
+                if (wi++ >= env_warm || n_blocks_total - done <= span * 4) break;
                 if ((rc = scan_range(s, p, done, done + span, bpi_main, lane))) return rc;
                 done += span;
             }
