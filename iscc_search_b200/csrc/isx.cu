@@ -185,6 +185,7 @@ struct isx_store {
     isx_stats_t stats{};
     int sm_count = 148;
     int max_smem_optin = 0;
+    int smem_per_sm = 0;
 };
 
 namespace isx {
@@ -366,9 +367,18 @@ static int build_tables(isx_store* s, uint32_t mask) {
 
 // ---- scan launch dispatch ----------------------------------------------------------------------
 template <int WE, int G, int MINB = 3>
-static int launch_scan_t(isx_store* s, const ScanParams& p, uint32_t grid_cap_per_sm, cudaStream_t stream) {
+static int launch_scan_t(isx_store* s, ScanParams& p, uint32_t grid_cap_per_sm, cudaStream_t stream) {
     constexpr int QW = (WE <= 4) ? 4 : 8;
     size_t smem = (size_t)p.q_split * (QW * 4 + 2) + 4 + 258 * 2 + ((size_t)p.R + 2) * 2 + 32;
+    // candidate stage (kernels.cuh "staged emission"): as many records as keep MINB CTAs of this size on an SM, at most 1024
+    {
+        static const int env_stage = [] { const char* e = getenv("ISX_STAGE"); return e ? atoi(e) : 1024; }();
+        const size_t per_cta = (size_t)s->smem_per_sm / MINB - 1024;   // the driver reserves 1 KB per CTA
+        size_t cap = per_cta > smem + stage_bytes(0) ? (per_cta - smem - stage_bytes(0)) / 12 : 0;
+        cap = std::min<size_t>(cap, (size_t)std::max(0, env_stage)) & ~(size_t)31;
+        p.stage_cap = cap >= 64 ? (uint32_t)cap : 0;
+        if (p.stage_cap) smem += stage_bytes(p.stage_cap);
+    }
     static bool attr_done = false;
     if (!attr_done || smem > 48 * 1024) {
         CU(cudaFuncSetAttribute(k_scan<WE, G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem_optin));
@@ -1036,6 +1046,7 @@ int isx_open(isx_store_t** out, int device, uint32_t key_bytes, uint32_t max_byt
     if (prop.major < 10) { delete s; return fail(ISX_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor); }
     s->sm_count = prop.multiProcessorCount;
     s->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    s->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
     s->small_ok = prop.cooperativeLaunch != 0;
     if (cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete s; return fail(ISX_ECUDA, "cudaStreamCreate failed"); }
     s->stream = s->own_stream;

@@ -65,6 +65,7 @@ struct ScanParams {
     uint32_t tighten_shift;      // a query's threshold is re-derived whenever its candidate count crosses a multiple of 2^shift
     uint32_t q_split;            // queries per CTA along gridDim.y (small ranges are split over queries
                                  // so the bootstrap rounds still fill the chip)
+    uint32_t stage_cap;          // candidate records a CTA stages in shared memory between two flushes (0: emit straight to HBM)
     // Cross-rank threshold sharing (multi-GPU): rank histograms of ALL ranks are summed in peer memory
     // over NVLink (CUDA IPC mapped). Query gq = g_q0 + q lives on rank gq % g_world, slot gq / g_world.
     // Every emission is also counted there (fire-and-forget remote RED); thresholds are tightened from the
@@ -173,6 +174,108 @@ __device__ __noinline__ void emit_group(const ScanParams& p, uint32_t q, uint32_
         __threadfence();   // this warp's own counts are visible to the sweep (others' are at worst missed: under-count)
         tighten_tau(p, q, lane);
     }
+}
+
+// ---- staged emission ---------------------------------------------------------------------------
+// emit_group pays one RETURNING global atomic (a round trip to L2, ~1 us with the warp stalled) per emitting row slot.
+// While the thresholds are loose - the warm-up ranges of every tile, the first items of the bulk launch, k = 1000 - that
+// round trip, not the popcounts, bounds the scan. So a CTA appends its candidates to a shared-memory stage (one
+// shared-memory atomic each) and flushes the stage at the end of every work item with all 256 threads: the slot
+// allocations of a whole item are in flight together, and the threshold is re-derived there. Thresholds are only re-read
+// at item boundaries anyway, so deferring the histogram updates to the same point changes nothing a CTA can observe.
+// A record that finds the stage full is written straight to HBM (stage_direct), so capacity never affects the result.
+// A record that finds the stage full is written straight to HBM (stage_direct), so capacity never affects the result;
+// if such a record crosses a tighten milestone, its query is noted in a short pending list that the flush serves too.
+// Layout behind the tables of k_scan: u64 cand[cap] | u32 query[cap] | u32 counters[4] | u32 pending[kStagePending].
+// The counters only grow: [0] records appended, [1] records flushed, [2] pending noted, [3] pending served - a flush
+// moves [1] and [3] up between two barriers, emitters (which run outside that window) index relative to them.
+constexpr uint32_t kStagePending = 32;
+struct Stage {
+    uint64_t* cand;
+    uint32_t* query;
+    uint32_t* counters;
+    uint32_t* pending;
+};
+__host__ __device__ constexpr size_t stage_bytes(uint32_t cap) { return 8 + (size_t)cap * 12 + 16 + kStagePending * 4; }
+__device__ __forceinline__ Stage stage_of(const ScanParams& p, const uint16_t* s_rank) {
+    uintptr_t a = (reinterpret_cast<uintptr_t>(s_rank + 258 + p.R) + 7) & ~(uintptr_t)7;
+    Stage st;
+    st.cand = reinterpret_cast<uint64_t*>(a);
+    st.query = reinterpret_cast<uint32_t*>(st.cand + p.stage_cap);
+    st.counters = st.query + p.stage_cap;
+    st.pending = st.counters + 4;
+    return st;
+}
+
+// one candidate of query q to HBM, by one thread; returns whether the query's count crossed a tighten milestone
+__device__ __forceinline__ bool stage_direct(const ScanParams& p, uint32_t q, uint64_t c) {
+    const uint32_t rank = cand_rank(c);
+    const uint32_t slot = atomicAdd(&p.cand_cnt[q], 1u);
+    atomicAdd(&p.hist[(size_t)q * p.R + rank], 1u);
+    if (p.g_world) {
+        const uint32_t gq = p.g_q0 + q;
+        atomicAdd(&p.g_hist[gq % p.g_world][(size_t)(gq / p.g_world) * p.g_rcap + rank], 1u);  // NVLink RED
+    }
+    if (slot < p.C) p.cand[(size_t)q * p.C + slot] = c;
+    else p.overflow[q] = 1u;
+    return ((slot + 1) >> p.tighten_shift) != (slot >> p.tighten_shift);
+}
+
+// entered by the whole warp when any lane has a row of the group within the bound of query q
+__device__ __noinline__ void stage_group(const ScanParams& p, uint32_t q, uint32_t hmax, uint32_t d0, uint32_t d1, uint32_t d2,
+                                         uint32_t d3, uint32_t seg, uint32_t row0, uint32_t seg_n, const uint16_t* s_rank) {
+    if (p.stage_cap == 0) {   // no room for a stage next to a maximal query tile: the warp-aggregated direct path
+        emit_group(p, q, hmax, d0, d1, d2, d3, seg, row0, seg_n, s_rank, nullptr);
+        return;
+    }
+    const Stage st = stage_of(p, s_rank);
+    const uint32_t d[4] = {d0, d1, d2, d3};
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        if (d[r] <= hmax && row0 + r < seg_n) {   // padding rows of the last block never emit
+            const uint64_t c = pack_cand(s_rank[d[r]], d[r], seg, row0 + r);
+            const uint32_t idx = atomicAdd(&st.counters[0], 1u) - st.counters[1];
+            if (idx < p.stage_cap) {
+                st.cand[idx] = c;
+                st.query[idx] = q;
+            } else if (stage_direct(p, q, c)) {
+                const uint32_t j = atomicAdd(&st.counters[2], 1u) - st.counters[3];
+                if (j < kStagePending) st.pending[j] = q;   // beyond that: the threshold just stays looser for a while
+            }
+        }
+    }
+}
+
+// all threads of the CTA, called between two barriers with no emitter in between
+__device__ __noinline__ void stage_flush(const ScanParams& p, const uint16_t* s_rank) {
+    const Stage st = stage_of(p, s_rank);
+    const uint32_t appended = st.counters[0], noted = st.counters[2];
+    const uint32_t n = min(appended - st.counters[1], p.stage_cap);
+    const uint32_t n_pending = min(noted - st.counters[3], kStagePending);
+    if (appended == st.counters[1] && n_pending == 0) return;   // CTA-uniform: nothing staged since the last flush
+    __syncthreads();                                            // everyone has read the counters
+    if (threadIdx.x == 0) { st.counters[1] = appended; st.counters[3] = noted; }
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t i0 = threadIdx.x & ~31u; i0 < n; i0 += kThreads) {   // warp-uniform trip count
+        const uint32_t i = i0 + lane;
+        uint32_t q = 0;
+        bool crossed = false;
+        if (i < n) {
+            q = st.query[i];
+            crossed = stage_direct(p, q, st.cand[i]);
+        }
+        if (p.update_tau) {
+            unsigned bal = __ballot_sync(0xffffffffu, crossed);
+            if (bal) __threadfence();   // this warp's counts are visible to its sweeps (others' are at worst missed: under-count)
+            while (bal) {
+                const int l = __ffs(bal) - 1;
+                bal &= bal - 1;
+                tighten_tau(p, __shfl_sync(0xffffffffu, q, l), lane);
+            }
+        }
+    }
+    if (p.update_tau)
+        for (uint32_t j = threadIdx.x >> 5; j < n_pending; j += kThreads / 32) tighten_tau(p, st.pending[j], lane);
 }
 
 // Hamming distance of one row (word r of each plane vector) to the query, WE words, last word masked.
@@ -285,6 +388,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_scan(const __grid_constant__
     const uint16_t* hrow = s_hrow;
     for (uint32_t i = tid; i < 257; i += kThreads) s_rank[i] = p.rank_tab[m * 257 + i];
     for (uint32_t i = tid; i < p.R; i += kThreads) s_hrow[i] = p.hmax_tab[(size_t)m * p.R + i];
+    if (p.stage_cap && tid < 4) stage_of(p, s_rank).counters[tid] = 0;
     __syncthreads();
 
     // shares are whole groups of G blocks, so only the launch's very last group can be partial (a partial group costs a
@@ -307,7 +411,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_scan(const __grid_constant__
     uint32_t n_items_done = 0;
     for (uint32_t b_lo = my_lo; b_lo < my_hi; n_items_done++) {
         const uint32_t b_hi = min(b_lo + item_blocks, my_hi);
-        __syncthreads();  // previous item's readers of hm are done
+        __syncthreads();  // previous item's readers of hm are done, its candidates are staged
+        if (p.stage_cap) stage_flush(p, s_rank);
         if (prefetch && n_items_done >= 3) {                  // steady state: bound fetched during the previous item
             if (tid < T) { if (kInRec) qw[(size_t)tid * QW + QW - 1] = hm_next; else hm[tid] = hm_next; }
         } else {                                              // ramp-up items: always the freshest bound
@@ -371,7 +476,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_scan(const __grid_constant__
                     }
                     const uint32_t dmin = min(min(d[0], d[1]), min(d[2], d[3]));
                     if (__any_sync(0xffffffffu, dmin <= hmax))
-                        emit_group(p, q0 + q, hmax, d[0], d[1], d[2], d[3], seg_id[g], row0[g], seg_n[g], s_rank, nullptr);
+                        stage_group(p, q0 + q, hmax, d[0], d[1], d[2], d[3], seg_id[g], row0[g], seg_n[g], s_rank);
                 };
                 auto bound_of = [&](int g) -> uint32_t {
                     return (LowerBound<WE>::kCutoff3 && tier == 3) ? LowerBound<WE>::template min4<3>(a[g], qv, mask_last)
@@ -401,6 +506,10 @@ __global__ void __launch_bounds__(kThreads, MINB) k_scan(const __grid_constant__
 
         b_lo = b_hi;
         item_blocks = min(item_blocks * 2, p.blocks_per_item);
+    }
+    if (p.stage_cap) {
+        __syncthreads();
+        stage_flush(p, s_rank);
     }
 }
 
