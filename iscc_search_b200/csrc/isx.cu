@@ -815,9 +815,15 @@ static int search_core(isx_store* s, const uint8_t* queries, bool q_on_device, c
         p.rank_tab = tb.d_rank.as<uint16_t>();
         p.hmax_tab = tb.d_hmax.as<uint16_t>();
         p.update_tau = 1;
-        {   // threshold feedback every ~k/4 new candidates of a query (power of two, >= 16)
-            uint32_t step = std::max<uint32_t>(k / 4, 16), sh = 0;
+        {   // threshold feedback every 2^sh new candidates of a query: ~k/4, at least 16. A small store on its own (no shared
+            // thresholds) re-derives less often, at the first power of two >= 2k: with the staged emission a re-derivation
+            // costs more there than the few candidates it saves (12.5 M rows, k = 100: 16 -> 73.8 ms per step, 64 -> 72.8,
+            // 256 -> 70.8, 1024 -> 73.4), while at 100 M rows 256 is 0.7 % slower than 16 and on 2 GPUs with shared thresholds
+            // 16..256 measure the same (profiles/r02m_shift_sweep.txt, r02m_n2_shift.txt, r02n_cfg3_n1.json)
+            const bool sparse_feedback = !share_on && s->n_rows <= (32u << 20);
+            uint32_t step = sparse_feedback ? std::max<uint32_t>(2 * k, 16) : std::max<uint32_t>(k / 4, 16), sh = 0;
             while ((2u << sh) <= step) sh++;
+            if (sparse_feedback && (1u << sh) < step) sh++;
             static const int env_shift = [] { const char* e = getenv("ISX_TIGHTEN_SHIFT"); return e ? atoi(e) : -1; }();
             p.tighten_shift = env_shift >= 0 ? (uint32_t)env_shift : sh;
         }
