@@ -183,7 +183,6 @@ __device__ __noinline__ void emit_group(const ScanParams& p, uint32_t q, uint32_
 // shared-memory atomic each) and flushes the stage at the end of every work item with all 256 threads: the slot
 // allocations of a whole item are in flight together, and the threshold is re-derived there. Thresholds are only re-read
 // at item boundaries anyway, so deferring the histogram updates to the same point changes nothing a CTA can observe.
-// A record that finds the stage full is written straight to HBM (stage_direct), so capacity never affects the result.
 // A record that finds the stage full is written straight to HBM (stage_direct), so capacity never affects the result;
 // if such a record crosses a tighten milestone, its query is noted in a short pending list that the flush serves too.
 // Layout behind the tables of k_scan: u64 cand[cap] | u32 query[cap] | u32 counters[4] | u32 pending[kStagePending].
