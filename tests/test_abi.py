@@ -79,3 +79,26 @@ def test_share_api_validates_arguments():
     assert L.isx_share_init(None, 2, 0, 16, buf) == _lib.ISX_EINVAL
     assert L.isx_share_attach(None, 1, buf) == _lib.ISX_EINVAL
     assert L.isx_share_reset(None) == _lib.ISX_EINVAL
+
+
+def test_header_is_plain_c_and_a_c_client_links(tmp_path):
+    """include/isx.h is C99 (what cgo / JNI / N-API bind), and examples/isx_client.c builds against the library with gcc alone.
+    Without a CUDA device the client must stop at isx_open with the library's message - no CPU path behind the ABI."""
+    import shutil
+    import subprocess
+
+    import torch
+
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc is part of this image"
+    exe = tmp_path / "isx_client"
+    so_dir = ROOT / "iscc_search_b200"
+    cmd = [gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", f"-I{ROOT / 'include'}", str(ROOT / "examples" / "isx_client.c"),
+           "-o", str(exe), f"-L{so_dir}", "-lisx_b200", f"-Wl,-rpath,{so_dir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    if torch.cuda.is_available():
+        return  # with a device the client really searches; its output is covered by the GPU suite's parity tests
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 2
+    assert "isx_open failed" in run.stderr and "no CPU fallback" in run.stderr
