@@ -98,7 +98,7 @@ def test_header_is_plain_c_and_a_c_client_links(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     if torch.cuda.is_available():
-        return  # with a device the client really searches; its output is covered by the GPU suite's parity tests
+        return  # with a device the client really searches: tests/test_gpu_c_client.py
     run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert run.returncode == 2
     assert "isx_open failed" in run.stderr and "no CPU fallback" in run.stderr
